@@ -1,0 +1,72 @@
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def rel_fro(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    den = b.norm().item()
+    return (a - b).norm().item() / (den if den > 0 else 1.0)
+
+
+def load_fixture(name):
+    return torch.load(os.path.join(GOLDEN, name + '.pt'), weights_only=False)
+
+
+MODELS = {}
+
+
+def model_for(name):
+    from oracle.models import SmallConvNet, TinyModel
+    return TinyModel() if name.startswith('tiny') else SmallConvNet()
+
+
+def loss_for(name):
+    if name.startswith('tiny'):
+        return torch.nn.MSELoss(reduction='sum')
+    return torch.nn.CrossEntropyLoss()
+
+
+def replay(name, make_precond, device='cpu', get_layers=None):
+    """Replay a golden fixture through a preconditioner implementation.
+
+    make_precond(model, **kwargs) -> object with .step(); get_layers(pre) ->
+    {layer_name: (A, G)} after each step.  Yields (step_idx, golden_step,
+    model, pre) after every step().
+    """
+    fx = load_fixture(name)
+    model = model_for(name)
+    model.load_state_dict(fx['init'])
+    model.to(device)
+    pre = make_precond(model, **fx['kwargs'])
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    loss_fn = loss_for(name)
+    bi = 0
+    for s in range(fx['steps']):
+        opt.zero_grad()
+        for _ in range(fx['micro']):
+            x, y = fx['batches'][bi % len(fx['batches'])]
+            bi += 1
+            loss_fn(model(x.to(device)), y.to(device)).backward()
+        pre.step()
+        yield s, fx['record'][s], model, pre
+        opt.step()
+
+
+@pytest.fixture
+def golden_names():
+    return ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
+            'conv_eigen', 'conv_inverse', 'conv_accum']

@@ -1,0 +1,56 @@
+"""Pins the CPU oracle against the reference-generated golden fixtures and
+the reference's own exact vectors (tests/layers/utils_test.py:25-72)."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_fro, replay
+from oracle import kfac_oracle as O
+
+NAMES = ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
+         'conv_eigen', 'conv_inverse', 'conv_accum']
+
+
+def test_get_cov_reference_vectors():
+    # exact vectors held by the reference: tests/layers/utils_test.py:25-72
+    a = torch.tensor([[1., 2, 3], [4, 5, 6], [7, 8, 9]])
+    assert torch.equal(O.get_cov(a, scale=1.0),
+                       torch.tensor([[66., 78, 90], [78, 93, 108], [90, 108, 126]]))
+    assert torch.equal(O.get_cov(a), torch.tensor([[22., 26, 30], [26, 31, 36], [30, 36, 42]]))
+    assert torch.equal(O.get_cov(torch.ones(2, 2)), torch.ones(2, 2))
+    c = O.get_cov(torch.randn(7, 5))
+    assert torch.equal(c, c.t())
+    with pytest.raises(ValueError):
+        O.get_cov(torch.ones(3))
+
+
+def _mk(model, **kw):
+    method = str(kw.pop('compute_method', 'eigen')).lower()
+    prediv = kw.pop('compute_eigenvalue_outer_product', True)
+    return O.OraclePreconditioner(model, compute_method=method, prediv=prediv, **kw)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_oracle_matches_reference(name):
+    worst = 0.0
+    for s, gold, model, pre in replay(name, _mk):
+        by_name = {L.name: L for L in pre.layers.values()}
+        for lname, g in gold['layers'].items():
+            L = by_name[lname]
+            assert rel_fro(L.A, g['A']) < 1e-6, (s, lname, 'A')
+            assert rel_fro(L.G, g['G']) < 1e-6, (s, lname, 'G')
+            e = rel_fro(L.P, g['P'])
+            worst = max(worst, e)
+            assert e < 2e-4, (s, lname, 'P', e)
+        assert abs(pre.last_scale - gold['scale']) <= 1e-4 * abs(gold['scale'])
+        for n, p in model.named_parameters():
+            assert rel_fro(p.grad, gold['final_grads'][n]) < 2e-4, (s, n)
+    print(name, 'worst P rel-fro', worst)
+
+
+def test_golden_assignment_file_is_sane():
+    with open(os.path.join(GOLDEN, 'kaisa_assignment.json')) as f:
+        d = json.load(f)
+    assert len(d['table']) > 100
