@@ -1,0 +1,480 @@
+// K5: batched symmetric (PSD) eigendecomposition by Jacobi rotations.
+//
+// Size classes
+//   n <= 64 / n <= 128 : the whole matrix lives in shared memory of ONE CTA;
+//                        two-sided cyclic Jacobi with a round-robin ordering
+//                        (N/2 disjoint rotations per step, N-1 steps / sweep).
+//   n  > 128           : block ONE-SIDED Jacobi (Hestenes) on G = F V:
+//                        per round, for every disjoint pair of 32-column blocks
+//                        (I,J): M = [G_I G_J]^T [G_I G_J] (64x64 Gram, GEMM) ->
+//                        W = eigvecs(M) (shared-memory Jacobi, as above) ->
+//                        [G_I G_J] <- [G_I G_J] W, [V_I V_J] <- [V_I V_J] W
+//                        (GEMM).  At convergence the columns of G are
+//                        orthogonal: lambda_j = |g_j|, Q = V.
+// All matrices of a batch advance through the rounds concurrently (one launch
+// per phase for the whole batch); per-matrix `done` flags computed on the
+// device make converged matrices drop out without a host sync.
+#include "common.cuh"
+
+#include <vector>
+
+namespace kfac {
+
+constexpr int JB = 32;        // block width
+constexpr int JP = 2 * JB;    // pair width
+constexpr int GR = 256;       // rows of G handled per CTA in gram/apply
+
+struct EighMat {
+  const float* F; float* Q; float* d;
+  float* G; float* V;          // np x np
+  float* M; float* W;          // pairs x JP x JP
+  int* pair_skip;              // pairs
+  int n, np, nb, pair_base, mode;
+  float tol;
+  unsigned int sweep_off;      // float bits, atomicMax
+  int done;
+  int sweeps;
+};
+
+// round-robin tournament: pair k of round r among nb (even) players
+__device__ __forceinline__ void tournament(int r, int k, int nb, int& p, int& q) {
+  const int m = nb - 1;
+  int a, b;
+  if (k == 0) { a = r % m; b = m; }
+  else { a = (r + k) % m; b = (r - k + m) % m; }
+  p = min(a, b); q = max(a, b);
+}
+
+__device__ __forceinline__ float rel_off(float apq, float app, float aqq) {
+  const float den = sqrtf(fabsf(app * aqq));
+  const float x = fabsf(apq);
+  if (x == 0.f) return 0.f;
+  return den > 0.f ? x / den : 1e30f;
+}
+
+// ------------------------------------------------------------ init / final
+__global__ void eigh_init_kernel(EighMat* mats, const int* block_list) {
+  EighMat& mt = mats[block_list[blockIdx.y]];
+  const int np = mt.np, n = mt.n;
+  const int64_t total = (int64_t)np * np;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / np), j = (int)(idx % np);
+    mt.G[idx] = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
+    mt.V[idx] = (i == j) ? 1.f : 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; }
+}
+
+__global__ void eigh_final_kernel(EighMat* mats, const int* block_list) {
+  EighMat& mt = mats[block_list[blockIdx.y]];
+  const int np = mt.np, n = mt.n;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // 32 x 8
+  for (int j0 = blockIdx.x * 32; j0 < n; j0 += gridDim.x * 32) {
+    const int j = j0 + tx;
+    float ss = 0.f;
+    for (int i = ty; i < n; i += 8) {
+      if (j < n) {
+        const float g = mt.G[(int64_t)i * np + j];
+        ss = fmaf(g, g, ss);
+        mt.Q[(int64_t)i * n + j] = mt.V[(int64_t)i * np + j];
+      }
+    }
+    red[ty][tx] = ss;
+    __syncthreads();
+    if (ty == 0 && j < n) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][tx];
+      mt.d[j] = sqrtf(t);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ gram
+__global__ void __launch_bounds__(256) eigh_gram_kernel(EighMat* mats, const int* pair_mat, int round) {
+  const int p = blockIdx.x;
+  EighMat& mt = mats[pair_mat[p]];
+  if (mt.done) return;
+  const int np = mt.np, n = mt.n;
+  const int r0c = blockIdx.y * GR;
+  if (r0c >= n) return;
+  const int r1c = min(n, r0c + GR);
+  const int local = p - mt.pair_base;
+  int I, J;
+  tournament(round % (mt.nb - 1), local, mt.nb, I, J);
+  __shared__ __align__(16) float Xs[16][JP + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const float* __restrict__ G = mt.G;
+  for (int r0 = r0c; r0 < r1c; r0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid % 64, r = tid / 64 + 4 * i;
+      const int col = (c < JB) ? (I * JB + c) : (J * JB + c - JB);
+      Xs[r][c] = (r0 + r < r1c) ? G[(int64_t)(r0 + r) * np + col] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Xs[k][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* M = mt.M + (int64_t)local * JP * JP;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&M[(ty * 4 + i) * JP + tx * 4 + j], acc[i][j]);
+}
+
+// --------------------------------------------------- shared-memory Jacobi
+// mode_block = 1: blockIdx.x = global pair index, M read from (and zeroed in)
+//                 the pair buffer, W written to the pair buffer.
+// mode_block = 0: blockIdx.x indexes `list`; the matrix itself is solved,
+//                 Q and d written directly.
+template <int N>
+__global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const int* list,
+                                                           int mode_block, int max_inner) {
+  extern __shared__ float sm[];
+  float (*M)[N + 1] = reinterpret_cast<float (*)[N + 1]>(sm);
+  float (*W)[N + 1] = reinterpret_cast<float (*)[N + 1]>(sm + N * (N + 1));
+  float* cs = sm + 2 * N * (N + 1);       // c[N/2], s[N/2]
+  __shared__ float redmax[32];
+  constexpr int T = N * 4;
+  const int tid = threadIdx.x;
+  EighMat& mt = mats[list[blockIdx.x]];
+  int local = 0;
+  float* Mg = nullptr;
+  if (mode_block) {
+    if (mt.done) return;
+    local = blockIdx.x - mt.pair_base;
+    Mg = mt.M + (int64_t)local * JP * JP;
+    for (int idx = tid; idx < N * N; idx += T) {
+      const int i = idx / N, j = idx % N;
+      M[i][j] = Mg[idx];
+      Mg[idx] = 0.f;
+      W[i][j] = (i == j) ? 1.f : 0.f;
+    }
+  } else {
+    const int n = mt.n;
+    for (int idx = tid; idx < N * N; idx += T) {
+      const int i = idx / N, j = idx % N;
+      M[i][j] = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
+      W[i][j] = (i == j) ? 1.f : 0.f;
+    }
+  }
+  __syncthreads();
+  const float tol = mt.tol;
+  if (mode_block) {
+    // largest relative off-diagonal of this pair's Gram (convergence measure)
+    float mx = 0.f;
+    for (int idx = tid; idx < N * N; idx += T) {
+      const int i = idx / N, j = idx % N;
+      if (j > i) mx = fmaxf(mx, rel_off(M[i][j], M[i][i], M[j][j]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) redmax[tid >> 5] = mx;
+    __syncthreads();
+    if (tid < 32) {
+      float v = (tid < T / 32) ? redmax[tid] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (tid == 0) redmax[0] = v;
+    }
+    __syncthreads();
+    mx = redmax[0];
+    if (tid == 0) {
+      atomicMax(&mt.sweep_off, __float_as_uint(mx));
+      mt.pair_skip[local] = (mx < tol) ? 1 : 0;
+    }
+    if (mx < tol) return;
+  }
+  const float tol_in = mode_block ? fminf(tol * 0.125f, 1e-6f) : 1e-7f;
+
+  for (int sweep = 0; sweep < max_inner; ++sweep) {
+    int rotated = 0;
+    for (int st = 0; st < N - 1; ++st) {
+      if (tid < N / 2) {
+        int p, q;
+        tournament(st, tid, N, p, q);
+        const float apq = M[p][q], app = M[p][p], aqq = M[q][q];
+        float c = 1.f, s = 0.f;
+        if (fabsf(apq) > tol_in * sqrtf(fabsf(app * aqq))) {
+          const float tau = (aqq - app) / (2.f * apq);
+          const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+          c = rsqrtf(1.f + t * t);
+          s = t * c;
+          if (s != 0.f) rotated = 1;
+        }
+        cs[tid] = c;
+        cs[N / 2 + tid] = s;
+      }
+      __syncthreads();
+      // column rotation of M and W
+      for (int idx = tid; idx < N * (N / 2); idx += T) {
+        const int i = idx % N, k = idx / N;
+        const float c = cs[k], s = cs[N / 2 + k];
+        if (s == 0.f) continue;
+        int p, q;
+        tournament(st, k, N, p, q);
+        const float x = M[i][p], y = M[i][q];
+        M[i][p] = c * x - s * y;
+        M[i][q] = s * x + c * y;
+        const float u = W[i][p], v = W[i][q];
+        W[i][p] = c * u - s * v;
+        W[i][q] = s * u + c * v;
+      }
+      __syncthreads();
+      // row rotation of M
+      for (int idx = tid; idx < N * (N / 2); idx += T) {
+        const int j = idx % N, k = idx / N;
+        const float c = cs[k], s = cs[N / 2 + k];
+        if (s == 0.f) continue;
+        int p, q;
+        tournament(st, k, N, p, q);
+        const float x = M[p][j], y = M[q][j];
+        M[p][j] = c * x - s * y;
+        M[q][j] = s * x + c * y;
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) break;
+  }
+
+  if (mode_block) {
+    float* Wg = mt.W + (int64_t)local * JP * JP;
+    for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx / N][idx % N];
+  } else {
+    const int n = mt.n;
+    for (int idx = tid; idx < n * n; idx += T) {
+      const int i = idx / n, j = idx % n;
+      mt.Q[idx] = W[i][j];
+    }
+    for (int j = tid; j < n; j += T) mt.d[j] = fmaxf(M[j][j], 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ apply
+__global__ void __launch_bounds__(256) eigh_apply_kernel(EighMat* mats, const int* pair_mat, int round) {
+  const int p = blockIdx.x;
+  EighMat& mt = mats[pair_mat[p]];
+  if (mt.done) return;
+  const int local = p - mt.pair_base;
+  if (mt.pair_skip[local]) return;
+  const int np = mt.np, n = mt.n;
+  const int r0c = blockIdx.y * GR;
+  if (r0c >= n) return;
+  const int r1c = min(n, r0c + GR);
+  int I, J;
+  tournament(round % (mt.nb - 1), local, mt.nb, I, J);
+  float* X = blockIdx.z ? mt.V : mt.G;
+  __shared__ __align__(16) float Ws[JP][JP + 4];
+  __shared__ float Xs[64][JP + 1];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const float* Wg = mt.W + (int64_t)local * JP * JP;
+  for (int idx = tid; idx < JP * JP; idx += 256) Ws[idx / JP][idx % JP] = Wg[idx];
+  for (int r0 = r0c; r0 < r1c; r0 += 64) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = tid % 64, r = tid / 64 + 4 * i;
+      const int col = (c < JB) ? (I * JB + c) : (J * JB + c - JB);
+      Xs[r][c] = (r0 + r < r1c) ? X[(int64_t)(r0 + r) * np + col] : 0.f;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < JP; ++k) {
+      const float4 b4 = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = Xs[ty * 4 + i][k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a, bv[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty * 4 + i;
+      if (r >= r1c) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = tx * 4 + j;
+        const int col = (c < JB) ? (I * JB + c) : (J * JB + c - JB);
+        X[(int64_t)r * np + col] = acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock, int round) {
+  for (int i = threadIdx.x; i < nblock; i += blockDim.x) {
+    EighMat& mt = mats[block_list[i]];
+    if (mt.done) continue;
+    if ((round + 1) % (mt.nb - 1) == 0) {
+      mt.sweeps += 1;
+      if (__uint_as_float(mt.sweep_off) < mt.tol) mt.done = 1;
+      mt.sweep_off = 0u;
+    }
+  }
+}
+
+// --------------------------------------------------------------- host side
+struct EighPlan {
+  std::vector<EighMat> mats;
+  std::vector<int> pair_mat, block_list, d64_list, d128_list;
+  size_t off_mats, off_pair_mat, off_block, off_d64, off_d128, off_data, total;
+  int total_pairs, max_nb, max_rows;
+};
+
+static void build_plan(const int* n, int count, EighPlan& pl) {
+  pl.mats.resize(count);
+  pl.total_pairs = 0; pl.max_nb = 0; pl.max_rows = 0;
+  for (int i = 0; i < count; ++i) {
+    EighMat& m = pl.mats[i];
+    m = EighMat{};
+    m.n = n[i];
+    if (n[i] <= 64) { m.mode = 0; pl.d64_list.push_back(i); }
+    else if (n[i] <= 128) { m.mode = 1; pl.d128_list.push_back(i); }
+    else {
+      m.mode = 2;
+      m.np = (n[i] + JP - 1) / JP * JP;
+      m.nb = m.np / JB;
+      m.pair_base = pl.total_pairs;
+      for (int k = 0; k < m.nb / 2; ++k) pl.pair_mat.push_back(i);
+      pl.total_pairs += m.nb / 2;
+      pl.max_nb = std::max(pl.max_nb, m.nb);
+      pl.max_rows = std::max(pl.max_rows, n[i]);
+      pl.block_list.push_back(i);
+    }
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  pl.off_mats = take(sizeof(EighMat) * count);
+  pl.off_pair_mat = take(sizeof(int) * std::max<size_t>(1, pl.pair_mat.size()));
+  pl.off_block = take(sizeof(int) * std::max<size_t>(1, pl.block_list.size()));
+  pl.off_d64 = take(sizeof(int) * std::max<size_t>(1, pl.d64_list.size()));
+  pl.off_d128 = take(sizeof(int) * std::max<size_t>(1, pl.d128_list.size()));
+  pl.off_data = off;
+  for (int i = 0; i < count; ++i) {
+    EighMat& m = pl.mats[i];
+    if (m.mode != 2) continue;
+    const size_t sq = (size_t)m.np * m.np * sizeof(float);
+    const size_t pb = (size_t)(m.nb / 2) * JP * JP * sizeof(float);
+    m.G = (float*)take(sq); m.V = (float*)take(sq);      // offsets, rebased later
+    m.M = (float*)take(pb); m.W = (float*)take(pb);
+    m.pair_skip = (int*)take(sizeof(int) * (m.nb / 2));
+  }
+  pl.total = off;
+}
+
+}  // namespace kfac
+
+using namespace kfac;
+
+extern "C" size_t kfac_eigh_workspace_bytes(const int* n, int count) {
+  if (!n || count <= 0) return 0;
+  EighPlan pl;
+  build_plan(n, count, pl);
+  return pl.total;
+}
+
+extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes,
+                                 int max_sweeps, float tol, void* stream) {
+  KFAC_CHECK_ARG(count >= 0 && (items || count == 0), "items");
+  if (count == 0) return KFAC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<int> ns(count);
+  for (int i = 0; i < count; ++i) {
+    KFAC_CHECK_ARG(items[i].F && items[i].Q && items[i].d && items[i].n > 0, "eigh item");
+    ns[i] = items[i].n;
+  }
+  EighPlan pl;
+  build_plan(ns.data(), count, pl);
+  if (!ws || ws_bytes < pl.total) {
+    set_error("eigh: workspace too small (%zu < %zu)", ws_bytes, pl.total);
+    return KFAC_ERR_WORKSPACE;
+  }
+  if (max_sweeps <= 0) max_sweeps = 16;
+  char* base = (char*)ws;
+  for (int i = 0; i < count; ++i) {
+    EighMat& m = pl.mats[i];
+    m.F = items[i].F; m.Q = items[i].Q; m.d = items[i].d;
+    m.tol = tol > 0.f ? tol : 1e-6f * sqrtf(fmaxf(1.f, (float)m.n / 16.f));
+    if (m.mode == 2) {
+      m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
+      m.M = (float*)(base + (size_t)m.M); m.W = (float*)(base + (size_t)m.W);
+      m.pair_skip = (int*)(base + (size_t)m.pair_skip);
+      KFAC_CUDA(cudaMemsetAsync(m.M, 0, (size_t)(m.nb / 2) * JP * JP * sizeof(float), s));
+    }
+  }
+  EighMat* d_mats = (EighMat*)(base + pl.off_mats);
+  int* d_pair_mat = (int*)(base + pl.off_pair_mat);
+  int* d_block = (int*)(base + pl.off_block);
+  int* d_d64 = (int*)(base + pl.off_d64);
+  int* d_d128 = (int*)(base + pl.off_d128);
+  KFAC_CUDA(cudaMemcpyAsync(d_mats, pl.mats.data(), sizeof(EighMat) * count, cudaMemcpyHostToDevice, s));
+  if (!pl.pair_mat.empty())
+    KFAC_CUDA(cudaMemcpyAsync(d_pair_mat, pl.pair_mat.data(), sizeof(int) * pl.pair_mat.size(), cudaMemcpyHostToDevice, s));
+  if (!pl.block_list.empty())
+    KFAC_CUDA(cudaMemcpyAsync(d_block, pl.block_list.data(), sizeof(int) * pl.block_list.size(), cudaMemcpyHostToDevice, s));
+  if (!pl.d64_list.empty())
+    KFAC_CUDA(cudaMemcpyAsync(d_d64, pl.d64_list.data(), sizeof(int) * pl.d64_list.size(), cudaMemcpyHostToDevice, s));
+  if (!pl.d128_list.empty())
+    KFAC_CUDA(cudaMemcpyAsync(d_d128, pl.d128_list.data(), sizeof(int) * pl.d128_list.size(), cudaMemcpyHostToDevice, s));
+  // the host vectors are pageable: cudaMemcpyAsync stages them before returning.
+
+  const size_t smem64 = (2 * 64 * 65 + 64) * sizeof(float);
+  const size_t smem128 = (2 * 128 * 129 + 128) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    KFAC_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
+    KFAC_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+    attr_set = true;
+  }
+  if (!pl.d64_list.empty()) {
+    jacobi_smem_kernel<64><<<(int)pl.d64_list.size(), 256, smem64, s>>>(d_mats, d_d64, 0, 24);
+    KFAC_LAUNCH_CHECK();
+  }
+  if (!pl.d128_list.empty()) {
+    jacobi_smem_kernel<128><<<(int)pl.d128_list.size(), 512, smem128, s>>>(d_mats, d_d128, 0, 24);
+    KFAC_LAUNCH_CHECK();
+  }
+  const int nblock = (int)pl.block_list.size();
+  if (nblock > 0) {
+    eigh_init_kernel<<<dim3(256, nblock), 256, 0, s>>>(d_mats, d_block);
+    KFAC_LAUNCH_CHECK();
+    const int rounds = max_sweeps * (pl.max_nb - 1);
+    const int chunks = ceil_div(pl.max_rows, GR);
+    for (int r = 0; r < rounds; ++r) {
+      eigh_gram_kernel<<<dim3(pl.total_pairs, chunks), 256, 0, s>>>(d_mats, d_pair_mat, r);
+      jacobi_smem_kernel<64><<<pl.total_pairs, 256, smem64, s>>>(d_mats, d_pair_mat, 1, 8);
+      eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
+      eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r);
+    }
+    KFAC_LAUNCH_CHECK();
+    eigh_final_kernel<<<dim3(64, nblock), 256, 0, s>>>(d_mats, d_block);
+    KFAC_LAUNCH_CHECK();
+  }
+  return KFAC_OK;
+}

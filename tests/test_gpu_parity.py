@@ -1,0 +1,182 @@
+"""End-to-end parity of KFACPreconditioner (CUDA path, through the C ABI)
+against (i) the reference-generated golden fixtures and (ii) the CPU oracle on
+the BASELINE.json workloads.  Bar: per-layer preconditioned gradient within
+1e-3 relative Frobenius (BASELINE.json north_star)."""
+import copy
+
+import pytest
+import torch
+
+from conftest import rel_fro, replay
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
+         'conv_eigen', 'conv_inverse', 'conv_accum']
+
+
+def _mk(model, **kw):
+    from kfac_b200.preconditioner import KFACPreconditioner
+    return KFACPreconditioner(model, **kw)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_golden_replay(name):
+    dev = torch.device('cuda:0')
+    worst = 0.0
+    for s, gold, model, pre in replay(name, _mk, device=dev):
+        torch.cuda.synchronize()
+        layers = {n: l for n, l in pre._layers.values()}
+        for lname, g in gold['layers'].items():
+            L = layers[lname]
+            assert rel_fro(L.a_factor, g['A']) < 2e-5, (s, lname, 'A')
+            assert rel_fro(L.g_factor, g['G']) < 2e-5, (s, lname, 'G')
+            e = rel_fro(L._p_view, g['P'])
+            worst = max(worst, e)
+            assert e < 1e-3, (s, lname, 'P', e)
+        scale = pre._compute_grad_scale()
+        assert abs(scale - gold['scale']) <= 1e-3 * abs(gold['scale']), (s, scale, gold['scale'])
+        for n, p in model.named_parameters():
+            assert rel_fro(p.grad, gold['final_grads'][n]) < 1e-3, (s, n)
+    print(name, 'worst P rel-fro vs reference', worst)
+
+
+def _parity_vs_oracle(make_model, x, y, loss_fn, steps, **kw):
+    from kfac_b200.preconditioner import KFACPreconditioner
+    from oracle.kfac_oracle import OraclePreconditioner
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    ref_model = make_model()
+    gpu_model = copy.deepcopy(ref_model).to(dev)
+    okw = dict(kw)
+    method = str(okw.pop('compute_method', 'eigen')).lower()
+    ref = OraclePreconditioner(ref_model, compute_method=method, **okw)
+    pre = KFACPreconditioner(gpu_model, **kw)
+    opt_r = torch.optim.SGD(ref_model.parameters(), lr=0.01)
+    opt_g = torch.optim.SGD(gpu_model.parameters(), lr=0.01)
+    xd, yd = x.to(dev), y.to(dev)
+    worst = 0.0
+    for s in range(steps):
+        opt_r.zero_grad()
+        opt_g.zero_grad()
+        loss_fn(ref_model(x), y).backward()
+        loss_fn(gpu_model(xd), yd).backward()
+        # feed the SAME raw gradients to both so only the K-FAC path is compared
+        for p, q in zip(ref_model.parameters(), gpu_model.parameters()):
+            q.grad.copy_(p.grad.to(dev))
+        ref.step()
+        pre.step()
+        torch.cuda.synchronize()
+        ref_layers = {L.name: L for L in ref.layers.values()}
+        for name, layer in pre._layers.values():
+            R = ref_layers[name]
+            assert rel_fro(layer.a_factor, R.A) < 1e-4, (s, name, 'A', rel_fro(layer.a_factor, R.A))
+            assert rel_fro(layer.g_factor, R.G) < 1e-4, (s, name, 'G', rel_fro(layer.g_factor, R.G))
+            e = rel_fro(layer._p_view, R.P)
+            worst = max(worst, e)
+            assert e < 1e-3, (s, name, 'P', e)
+        assert abs(pre._compute_grad_scale() - ref.last_scale) <= 1e-3 * ref.last_scale
+        opt_r.step()
+        # keep the two models in lock-step
+        for p, q in zip(ref_model.parameters(), gpu_model.parameters()):
+            q.data.copy_(p.data.to(dev))
+        for (bn, b), (_, c) in zip(ref_model.named_buffers(), gpu_model.named_buffers()):
+            c.data.copy_(b.data.to(dev))
+    return worst
+
+
+def test_resnet32_parity():
+    """BASELINE.json configs[1]: ResNet-32, CIFAR-shaped synthetic batch."""
+    from oracle.models import resnet32
+    torch.manual_seed(1)
+    x = torch.randn(32, 3, 32, 32)
+    y = torch.randint(0, 10, (32,))
+    worst = _parity_vs_oracle(resnet32, x, y, torch.nn.CrossEntropyLoss(), steps=3,
+                              damping=0.003, factor_decay=0.95, kl_clip=0.001, lr=0.1)
+    print('resnet32 worst P rel-fro', worst)
+
+
+def test_resnet32_inverse_method_parity():
+    from oracle.models import resnet32
+    torch.manual_seed(2)
+    x = torch.randn(16, 3, 32, 32)
+    y = torch.randint(0, 10, (16,))
+    worst = _parity_vs_oracle(resnet32, x, y, torch.nn.CrossEntropyLoss(), steps=2,
+                              damping=0.003, compute_method='inverse')
+    print('resnet32 inverse worst P rel-fro', worst)
+
+
+def test_bottleneck_stack_parity():
+    """ResNet-50-shaped layers at reduced width (the full model runs in bench.py)."""
+    from oracle.models import ResNet50
+    torch.manual_seed(3)
+    x = torch.randn(4, 3, 64, 64)
+    y = torch.randint(0, 10, (4,))
+    worst = _parity_vs_oracle(lambda: ResNet50(num_classes=10, width=16, blocks=(1, 1, 1, 1)), x, y,
+                              torch.nn.CrossEntropyLoss(), steps=2, damping=0.001)
+    print('bottleneck worst P rel-fro', worst)
+
+
+def test_state_dict_roundtrip_and_schedule():
+    from kfac_b200.preconditioner import KFACPreconditioner
+    from oracle.models import TinyModel
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    m = TinyModel().to(dev)
+    p = KFACPreconditioner(m, factor_update_steps=2, inv_update_steps=4)
+    x = torch.rand(4, 10, device=dev)
+    for _ in range(3):
+        m.zero_grad()
+        m(x).sum().backward()
+        p.step()
+    sd = p.state_dict()
+    assert sd['steps'] == 3 and set(sd['layers']) == {'linear1', 'linear2'}
+    assert sd['layers']['linear1']['A'].shape == (10, 10) and sd['layers']['linear2']['A'].shape == (21, 21)
+    m2 = TinyModel().to(dev)
+    p2 = KFACPreconditioner(m2, factor_update_steps=2, inv_update_steps=4)
+    p2.load_state_dict(sd)
+    assert p2.steps == 3
+    for (_, a), (_, b) in zip(p._layers.values(), p2._layers.values()):
+        assert torch.equal(a.a_factor, b.a_factor) and torch.equal(a.g_factor, b.g_factor)
+        assert b.qa is not None and b.qg is not None     # inverses recomputed on load
+    mem = p.memory_usage()
+    assert mem['total'] > 0 and set(mem) >= {'a_factors', 'g_factors', 'a_inverses', 'g_inverses', 'total'}
+    # hooks are inert in eval mode
+    m.eval()
+    before = p._layers[m.linear1][1]._a_count
+    m(x)
+    assert p._layers[m.linear1][1]._a_count == before
+
+
+def test_step_before_factors_raises():
+    from kfac_b200.preconditioner import KFACPreconditioner
+    from oracle.models import TinyModel
+    dev = torch.device('cuda:0')
+    m = TinyModel().to(dev)
+    p = KFACPreconditioner(m)
+    m.eval()
+    m(torch.rand(2, 10, device=dev)).sum().backward()
+    with pytest.raises(RuntimeError):
+        p.step()
+
+
+def test_training_loss_decreases():
+    """tests/training_test.py:15-55 of the reference: losses[0] > losses[-1]."""
+    from kfac_b200.preconditioner import KFACPreconditioner
+    from oracle.models import TinyModel
+    dev = torch.device('cuda:0')
+    torch.manual_seed(42)
+    m = TinyModel().to(dev)
+    opt = torch.optim.SGD(m.parameters(), lr=0.001)
+    p = KFACPreconditioner(m, lr=0.001)
+    x, y = torch.rand(4, 10, device=dev), torch.rand(4, 10, device=dev)
+    crit = torch.nn.MSELoss(reduction='sum')
+    losses = []
+    for _ in range(20):
+        opt.zero_grad()
+        loss = crit(m(x), y)
+        loss.backward()
+        p.step()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[0] > losses[-1]
