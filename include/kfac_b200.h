@@ -44,6 +44,8 @@ int kfac_version(void);
 const char* kfac_last_error(void);
 /* compute capability of the current device (e.g. 100) or <0 */
 int kfac_device_arch(void);
+/* cumulative number of CUDA kernels this library has launched in the process */
+long long kfac_launch_count(void);
 
 /* ---------------------------------------------------------------- factors
  * K3: second-moment statistics, accumulated into `acc` (d x d, fp32):

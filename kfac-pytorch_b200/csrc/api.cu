@@ -12,6 +12,8 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 }  // namespace kfac
 
 extern "C" int kfac_version(void) { return 100; /* 0.1.0 */ }
@@ -25,3 +27,5 @@ extern "C" int kfac_device_arch(void) {
   }
   return p.major * 10 + p.minor;
 }
+
+extern "C" long long kfac_launch_count(void) { return __atomic_load_n(&kfac::g_launches, __ATOMIC_RELAXED); }

@@ -11,6 +11,7 @@
 namespace kfac {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n);
 
 #define KFAC_CHECK_ARG(cond, msg)                         \
   do {                                                    \
@@ -30,7 +31,11 @@ void set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
-#define KFAC_LAUNCH_CHECK() KFAC_CUDA(cudaGetLastError())
+#define KFAC_LAUNCH_CHECK()            \
+  do {                                 \
+    ::kfac::count_launch(1);           \
+    KFAC_CUDA(cudaGetLastError());     \
+  } while (0)
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

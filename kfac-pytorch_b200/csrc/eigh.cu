@@ -472,6 +472,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
       eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
       eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r);
     }
+    count_launch(4 * rounds - 1);
     KFAC_LAUNCH_CHECK();
     eigh_final_kernel<<<dim3(64, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();

@@ -178,6 +178,7 @@ extern "C" int kfac_grad_scale(const kfac_grad_item* items, int count, float kl_
     vg_kernel<<<grid_for((int64_t)it.g * it.a), 256, 0, s>>>(it.P, it.wgrad, it.bgrad, it.grad_dtype,
                                                             it.g, it.a, scratch);
   }
+  count_launch(count - 1);
   KFAC_LAUNCH_CHECK();
   nu_kernel<<<1, 1, 0, s>>>(scratch, kl_clip, lr, scale_out);
   KFAC_LAUNCH_CHECK();
@@ -193,6 +194,7 @@ extern "C" int kfac_grad_update(const kfac_grad_item* items, int count, const fl
     update_kernel<<<grid_for((int64_t)it.g * it.a), 256, 0, s>>>(it.P, it.wgrad, it.bgrad, it.grad_dtype,
                                                                 it.g, it.a, scale);
   }
+  count_launch(count - 1);
   KFAC_LAUNCH_CHECK();
   return KFAC_OK;
 }
