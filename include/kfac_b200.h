@@ -99,10 +99,12 @@ int kfac_factor_ema(const kfac_ema_item* items, int count, float alpha,
  * order of Q's columns -- NOT sorted).  All matrices of the batch are solved
  * concurrently (block one-sided Jacobi; n <= 128 solved in shared memory). */
 typedef struct kfac_eigh_item {
-  const float* F;
-  float* Q;
+  const float* F; /* n x n dense (ld = n) */
+  float* Q;       /* n x n, leading dimension ldq */
+  float* QT;      /* optional transposed copy (rows are eigenvectors), ld = ldq; may be NULL */
   float* d;
   int n;
+  int ldq;        /* 0 -> n.  Multiples of 4 let the tensor-core GEMMs consume Q directly */
 } kfac_eigh_item;
 size_t kfac_eigh_workspace_bytes(const int* n, int count);
 /* max_sweeps <= 0 -> default (16); tol <= 0 -> automatic (scaled with sqrt(n)) */
@@ -111,13 +113,18 @@ int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* ws,
 
 /* K6: replaces eigen.py:345-348: out[i,j] = 1 / (dg[i]*da[j] + damping) */
 int kfac_dgda(const float* dg, const float* da, int g, int a, float damping,
-              float* out, void* stream);
+              float* out, int ld_out, void* stream);
 
 /* K7: replaces KFACInverseLayer.compute_{a,g}_inv (kfac/layers/inverse.py:
  * 186-213): inv = (F + damping I)^-1, formed as Q diag(1/(d+damping)) Q^T from
- * the eigendecomposition of F (F is symmetric PSD). ws: n*n floats. */
-int kfac_inverse_from_eigh(const float* Q, const float* d, int n, float damping,
-                           float* inv, void* ws, size_t ws_bytes, void* stream);
+ * the eigendecomposition of F (F is symmetric PSD). ws: n*ldq floats. */
+int kfac_inverse_from_eigh(const float* Q, int ldq, const float* d, int n,
+                           float damping, float* inv, int ld_inv, void* ws,
+                           size_t ws_bytes, void* stream);
+/* dst (cols x rows, ld_dst) = src^T (src rows x cols, ld_src): gives a rank that
+ * received an eigenbasis by broadcast the K-major copy the GEMM engine wants */
+int kfac_transpose(const float* src, int ld_src, float* dst, int ld_dst, int rows,
+                   int cols, void* stream);
 
 /* ---------------------------------------------------------- precondition
  * K8/K9/K10: replaces ModuleHelper.get_grad (modules.py:56-69,194-208) and
@@ -131,14 +138,18 @@ typedef struct kfac_precond_item {
   const void* bgrad; /* (g) or NULL */
   int grad_dtype;
   int g, a; /* a includes the bias column when bgrad != NULL */
-  const float* qa;
-  const float* qg;
-  const float* dgda; /* g x a or NULL */
+  const float* qa;   /* a x a (ld = ldqa), columns are eigenvectors */
+  const float* qaT;  /* its transpose (ld = ldqa) */
+  const float* qg;   /* g x g (ld = ldqg) */
+  const float* qgT;
+  const float* dgda; /* g x a (ld = ld_dgda) or NULL */
   const float* da;
   const float* dg;
-  const float* a_inv;
-  const float* g_inv;
-  float* P; /* out: g x a fp32 */
+  const float* a_inv; /* a x a (ld = ldqa), symmetric */
+  const float* g_inv; /* g x g (ld = ldqg), symmetric */
+  int ldqa, ldqg, ld_dgda;
+  float* P; /* out: g x a fp32 (ld = ldp) */
+  int ldp;
 } kfac_precond_item;
 size_t kfac_precondition_workspace_bytes(const kfac_precond_item* items, int count);
 int kfac_precondition(const kfac_precond_item* items, int count, int method,
@@ -156,6 +167,7 @@ typedef struct kfac_grad_item {
   void* bgrad;
   int grad_dtype;
   int g, a;
+  int ldp; /* leading dimension of P */
 } kfac_grad_item;
 /* scratch: device double[1] (vg) ; scale_out: device float[1] (nu) */
 int kfac_grad_scale(const kfac_grad_item* items, int count, float kl_clip,
@@ -179,6 +191,14 @@ int kfac_scale_inplace(float* buf, int64_t count, float s, void* stream);
 int kfac_gemm_f32(const float* A, int64_t sa_m, int64_t sa_k, const float* B,
                   int64_t sb_k, int64_t sb_n, float* C, int64_t ldc, int M,
                   int N, int K, float alpha, float beta, void* stream);
+
+/* Tensor-core engine (tcgen05 / TMA, 3xTF32 split, fp32 accumulate in TMEM):
+ * D (+)= alpha * A B^T with A (M x K) and B (N x K) row-major fp32, lda/ldb
+ * multiples of 4 and 16-byte aligned bases.  atomic != 0: accumulate into D
+ * with split-K (`splits` <= 0: automatic).  Exposed for tests / profiling. */
+int kfac_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb,
+                    float* D, int64_t ldd, int M, int N, int K, float alpha,
+                    int atomic, int splits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,20 +29,22 @@ class EmaItem(C.Structure):
 
 
 class EighItem(C.Structure):
-    _fields_ = [('F', c_void_p), ('Q', c_void_p), ('d', c_void_p), ('n', c_int)]
+    _fields_ = [('F', c_void_p), ('Q', c_void_p), ('QT', c_void_p), ('d', c_void_p), ('n', c_int), ('ldq', c_int)]
 
 
 class PrecondItem(C.Structure):
     _fields_ = [('wgrad', c_void_p), ('bgrad', c_void_p), ('grad_dtype', c_int),
                 ('g', c_int), ('a', c_int),
-                ('qa', c_void_p), ('qg', c_void_p), ('dgda', c_void_p),
-                ('da', c_void_p), ('dg', c_void_p),
-                ('a_inv', c_void_p), ('g_inv', c_void_p), ('P', c_void_p)]
+                ('qa', c_void_p), ('qaT', c_void_p), ('qg', c_void_p), ('qgT', c_void_p),
+                ('dgda', c_void_p), ('da', c_void_p), ('dg', c_void_p),
+                ('a_inv', c_void_p), ('g_inv', c_void_p),
+                ('ldqa', c_int), ('ldqg', c_int), ('ld_dgda', c_int),
+                ('P', c_void_p), ('ldp', c_int)]
 
 
 class GradItem(C.Structure):
     _fields_ = [('P', c_void_p), ('wgrad', c_void_p), ('bgrad', c_void_p),
-                ('grad_dtype', c_int), ('g', c_int), ('a', c_int)]
+                ('grad_dtype', c_int), ('g', c_int), ('a', c_int), ('ldp', c_int)]
 
 
 # name -> (restype, argtypes); must list EVERY symbol of include/kfac_b200.h
@@ -58,8 +60,9 @@ SIGNATURES = {
     'kfac_factor_ema': (c_int, [C.POINTER(EmaItem), c_int, c_float, c_void_p]),
     'kfac_eigh_workspace_bytes': (c_size_t, [C.POINTER(c_int), c_int]),
     'kfac_eigh_batched': (c_int, [C.POINTER(EighItem), c_int, c_void_p, c_size_t, c_int, c_float, c_void_p]),
-    'kfac_dgda': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
-    'kfac_inverse_from_eigh': (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'kfac_dgda': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
+    'kfac_inverse_from_eigh': (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    'kfac_transpose': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     'kfac_precondition_workspace_bytes': (c_size_t, [C.POINTER(PrecondItem), c_int]),
     'kfac_precondition': (c_int, [C.POINTER(PrecondItem), c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     'kfac_grad_scale': (c_int, [C.POINTER(GradItem), c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
@@ -67,6 +70,8 @@ SIGNATURES = {
     'kfac_triu_pack': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'kfac_triu_unpack': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'kfac_scale_inplace': (c_int, [c_void_p, c_int64, c_float, c_void_p]),
+    'kfac_gemm_tn_tc': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                c_float, c_int, c_int, c_void_p]),
     'kfac_gemm_f32': (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                               c_int, c_int, c_int, c_float, c_float, c_void_p]),
 }
@@ -110,6 +115,12 @@ def check(rc: int, what: str = '') -> None:
     if rc == KFAC_ERR_NOT_READY:
         raise RuntimeError(msg)
     raise KFACNativeError(f'{msg} (status {rc})')
+
+
+def ld4(n: int) -> int:
+    """Leading dimension used for arena matrices: multiple of 4 floats (16 B) so
+    TMA tensor maps can address them."""
+    return (n + 3) & ~3
 
 
 def stream_ptr() -> int:

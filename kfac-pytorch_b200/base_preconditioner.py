@@ -48,6 +48,19 @@ class _Scratch:
         return self.buf
 
 
+def _storage_numel(shape: tuple[int, ...]) -> int:
+    if len(shape) == 2:
+        return shape[0] * _cabi.ld4(shape[1])
+    return shape[0]
+
+
+def _bind(arena: torch.Tensor, off: int, shape: tuple[int, ...]) -> torch.Tensor:
+    """Storage tensor of one arena entry: (rows, ld4(cols)) or (n,)."""
+    n = _storage_numel(shape)
+    t = arena.narrow(0, off, n)
+    return t.view(shape[0], _cabi.ld4(shape[1])) if len(shape) == 2 else t
+
+
 class _Segment:
     """Contiguous arena slice moved by one broadcast: (group, src) -> tensors."""
 
@@ -59,11 +72,10 @@ class _Segment:
         self.numel = 0
 
     def add(self, layer: KFACLayer, key: str, shape: tuple[int, ...]) -> None:
+        """shape = logical shape; matrices are stored with a leading dimension
+        padded to a multiple of 4 floats (TMA-addressable rows)."""
         self.entries.append((layer, key, shape))
-        n = 1
-        for s in shape:
-            n *= s
-        self.numel += n
+        self.numel += _storage_numel(shape)
 
 
 def build_comm_plan(layers: list[tuple[str, KFACLayer]], assignment: WorkAssignment):
@@ -260,15 +272,14 @@ class BaseKFACPreconditioner:
             for s in segs:
                 off = s.offset
                 for layer, key, shape in s.entries:
-                    n = 1
-                    for d in shape:
-                        n *= d
-                    view = arena.narrow(0, off, n).view(*shape)
+                    store = _bind(arena, off, shape)
                     if key == 'P':
-                        layer._p_view = view
+                        layer._p_store = store
+                        layer._p_view = store[:, :shape[1]]
                     else:
-                        layer._inv[key] = view
-                    off += n
+                        layer._inv[key] = store
+                        layer._inv_cols[key] = shape[-1]
+                    off += _storage_numel(shape)
         # local (never communicated) eigen scratch of the inverse worker
         rank = get_rank()
         local = 0
@@ -277,6 +288,9 @@ class BaseKFACPreconditioner:
             mine_a = rank == self._assignment.inv_worker(name, 'A')
             mine_g = rank == self._assignment.inv_worker(name, 'G')
             if l.method == ComputeMethod.EIGEN:
+                if self._assignment.is_grad_worker(name):
+                    # K-major (transposed) copies of the eigenbases for the GEMM engine
+                    plan += [(l, '_qaT', (l.a_dim, l.a_dim)), (l, '_qgT', (l.g_dim, l.g_dim))]
                 if l.prediv_eigenvalues:
                     if mine_a:
                         plan.append((l, '_da', (l.a_dim,)))
@@ -288,18 +302,13 @@ class BaseKFACPreconditioner:
                 if mine_g:
                     plan += [(l, '_qg', (l.g_dim, l.g_dim)), (l, '_dg', (l.g_dim,))]
         for _, _, shape in plan:
-            n = 1
-            for d in shape:
-                n *= d
-            local += n
+            local += _storage_numel(shape)
         self._local_arena = torch.zeros(max(local, 1), dtype=torch.float32, device=device)
         off = 0
         for l, key, shape in plan:
-            n = 1
-            for d in shape:
-                n *= d
-            l._inv[key] = self._local_arena.narrow(0, off, n).view(*shape)
-            off += n
+            l._inv[key] = _bind(self._local_arena, off, shape)
+            l._inv_cols[key] = shape[-1]
+            off += _storage_numel(shape)
         self._vg = torch.zeros(1, dtype=torch.float64, device=device)
         self._nu = torch.ones(1, dtype=torch.float32, device=device)
         self._arenas_ready = True
@@ -446,7 +455,7 @@ class BaseKFACPreconditioner:
         rank = get_rank()
         damping = float(self.damping)
         stream = _cabi.stream_ptr()
-        eig: list[tuple[torch.Tensor, torch.Tensor, torch.Tensor, int]] = []
+        eig: list[tuple[torch.Tensor, torch.Tensor, torch.Tensor | None, torch.Tensor, int]] = []
         post: list[tuple[KFACLayer, str]] = []
         for name, layer in reversed(self._layer_list()):
             mine_a = rank == self._assignment.inv_worker(name, 'A')
@@ -459,27 +468,28 @@ class BaseKFACPreconditioner:
             if layer.method == ComputeMethod.EIGEN:
                 if layer.prediv_eigenvalues:
                     if mine_a:
-                        eig.append((layer._a_view, I['qa'], I['_da'], layer.a_dim))
+                        eig.append((layer._a_view, I['qa'], I['_qaT'], I['_da'], layer.a_dim))
                     if mine_g:
-                        eig.append((layer._g_view, I['qg'], I['_dg'], layer.g_dim))
+                        eig.append((layer._g_view, I['qg'], I['_qgT'], I['_dg'], layer.g_dim))
                         post.append((layer, 'dgda'))
                 else:
                     if mine_a:
-                        eig.append((layer._a_view, I['qa'], I['da'], layer.a_dim))
+                        eig.append((layer._a_view, I['qa'], I['_qaT'], I['da'], layer.a_dim))
                     if mine_g:
-                        eig.append((layer._g_view, I['qg'], I['dg'], layer.g_dim))
+                        eig.append((layer._g_view, I['qg'], I['_qgT'], I['dg'], layer.g_dim))
             else:
                 if mine_a:
-                    eig.append((layer._a_view, I['_qa'], I['_da'], layer.a_dim))
+                    eig.append((layer._a_view, I['_qa'], None, I['_da'], layer.a_dim))
                     post.append((layer, 'a_inv'))
                 if mine_g:
-                    eig.append((layer._g_view, I['_qg'], I['_dg'], layer.g_dim))
+                    eig.append((layer._g_view, I['_qg'], None, I['_dg'], layer.g_dim))
                     post.append((layer, 'g_inv'))
         if eig:
             items = (_cabi.EighItem * len(eig))()
             ns = (C.c_int * len(eig))()
-            for i, (F, Q, d, n) in enumerate(eig):
-                items[i] = _cabi.EighItem(F.data_ptr(), Q.data_ptr(), d.data_ptr(), n)
+            for i, (F, Q, QT, d, n) in enumerate(eig):
+                items[i] = _cabi.EighItem(F.data_ptr(), Q.data_ptr(), QT.data_ptr() if QT is not None else None,
+                                          d.data_ptr(), n, _cabi.ld4(n))
                 ns[i] = n
             need = lib.kfac_eigh_workspace_bytes(ns, len(eig))
             ws = self._eig_scratch.get(need, self._device)
@@ -489,13 +499,15 @@ class BaseKFACPreconditioner:
             I = layer._inv
             if what == 'dgda':
                 _cabi.check(lib.kfac_dgda(I['_dg'].data_ptr(), I['_da'].data_ptr(), layer.g_dim,
-                                          layer.a_dim, damping, I['dgda'].data_ptr(), stream), 'kfac_dgda')
+                                          layer.a_dim, damping, I['dgda'].data_ptr(),
+                                          _cabi.ld4(layer.a_dim), stream), 'kfac_dgda')
             else:
                 q, d, n = (I['_qa'], I['_da'], layer.a_dim) if what == 'a_inv' else (I['_qg'], I['_dg'], layer.g_dim)
-                need = n * n * 4
+                ld = _cabi.ld4(n)
+                need = n * ld * 4
                 ws = self._gemm_scratch.get(need, self._device)
-                _cabi.check(lib.kfac_inverse_from_eigh(q.data_ptr(), d.data_ptr(), n, damping,
-                                                       I[what].data_ptr(), ws.data_ptr(), need, stream),
+                _cabi.check(lib.kfac_inverse_from_eigh(q.data_ptr(), ld, d.data_ptr(), n, damping,
+                                                       I[what].data_ptr(), ld, ws.data_ptr(), need, stream),
                             'kfac_inverse_from_eigh')
         # C2: one broadcast per (source, gradient-worker group)
         bcast = self._assignment.broadcast_inverses()
@@ -503,8 +515,14 @@ class BaseKFACPreconditioner:
             if bcast:
                 self._tdc.broadcast(self._inv_arena.narrow(0, seg.offset, seg.numel), src=seg.src,
                                     group=seg.group)
-            for layer, key, _ in seg.entries:
+            for layer, key, shape in seg.entries:
                 layer._inv_ready.add(key)
+                # a rank that RECEIVED an eigenbasis builds its K-major copy locally
+                if bcast and seg.src != rank and key in ('qa', 'qg'):
+                    n, ld = shape[0], _cabi.ld4(shape[0])
+                    _cabi.check(lib.kfac_transpose(layer._inv[key].data_ptr(), ld,
+                                                   layer._inv['_' + key + 'T'].data_ptr(), ld, n, n, stream),
+                                'kfac_transpose')
 
     # K8/K9/K10 + C3 -------------------------------------------------------
     def _grad_ptrs(self, layer: KFACLayer):
@@ -540,10 +558,15 @@ class BaseKFACPreconditioner:
             def p(key):
                 return I[key].data_ptr() if key in ready else None
 
+            eig_ok = 'qa' in ready and 'qg' in ready
             items[i] = _cabi.PrecondItem(
                 w.data_ptr(), b.data_ptr() if b is not None else None, _cabi.DTYPE_CODE[w.dtype],
-                layer.g_dim, layer.a_dim, p('qa'), p('qg'), p('dgda'), p('da'), p('dg'),
-                p('a_inv'), p('g_inv'), layer._p_view.data_ptr())
+                layer.g_dim, layer.a_dim,
+                p('qa'), I['_qaT'].data_ptr() if eig_ok else None,
+                p('qg'), I['_qgT'].data_ptr() if eig_ok else None,
+                p('dgda'), p('da'), p('dg'), p('a_inv'), p('g_inv'),
+                _cabi.ld4(layer.a_dim), _cabi.ld4(layer.g_dim), _cabi.ld4(layer.a_dim),
+                layer._p_store.data_ptr(), _cabi.ld4(layer.a_dim))
         if todo:
             need = lib.kfac_precondition_workspace_bytes(items, len(todo))
             ws = self._gemm_scratch.get(need, self._device)
@@ -564,9 +587,10 @@ class BaseKFACPreconditioner:
         items = (_cabi.GradItem * max(1, len(ll)))()
         for i, (_, layer) in enumerate(ll):
             w, b = self._grad_ptrs(layer)
-            items[i] = _cabi.GradItem(layer._p_view.data_ptr(), w.data_ptr(),
+            items[i] = _cabi.GradItem(layer._p_store.data_ptr(), w.data_ptr(),
                                       b.data_ptr() if b is not None else None,
-                                      _cabi.DTYPE_CODE[w.dtype], layer.g_dim, layer.a_dim)
+                                      _cabi.DTYPE_CODE[w.dtype], layer.g_dim, layer.a_dim,
+                                      _cabi.ld4(layer.a_dim))
         stream = _cabi.stream_ptr()
         kl_clip = self.kl_clip
         scale_ptr = None

@@ -90,6 +90,20 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream);
 
 // tcgen05 engine (gemm_tc.cu); returns KFAC_ERR_UNSUPPORTED when the shape /
 // alignment is outside what the tensor-core kernel handles.
-struct TcGemmArgs;
+struct TcGemmArgs {
+  const float* A; int64_t lda;     // M x K row-major (K-major operand), lda % 4 == 0
+  const float* B; int64_t ldb;     // N x K row-major
+  float* D; int64_t ldd;           // M x N row-major
+  int M, N, K;
+  int kbatch;                      // reduction batches: D = sum_b A_b B_b^T
+  int64_t a_kb_stride, b_kb_stride;
+  int upper_only;                  // SYRK: compute tiles tn >= tm, mirror the rest
+  int atomic;                      // epilogue accumulates with atomicAdd (split-K)
+  int splits;                      // <= 0: automatic
+  float alpha;
+  int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
+};
+bool tc_gemm_supported(const TcGemmArgs& a);
+int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream);
 
 }  // namespace kfac

@@ -25,7 +25,8 @@ constexpr int JP = 2 * JB;    // pair width
 constexpr int GR = 256;       // rows of G handled per CTA in gram/apply
 
 struct EighMat {
-  const float* F; float* Q; float* d;
+  const float* F; float* Q; float* QT; float* d;
+  int ldq;
   float* G; float* V;          // np x np
   float* M; float* W;          // pairs x JP x JP
   int* pair_skip;              // pairs
@@ -70,25 +71,35 @@ __global__ void eigh_final_kernel(EighMat* mats, const int* block_list) {
   EighMat& mt = mats[block_list[blockIdx.y]];
   const int np = mt.np, n = mt.n;
   __shared__ float red[8][33];
+  __shared__ float redv[8][33];
   const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;  // 32 x 8
   for (int j0 = blockIdx.x * 32; j0 < n; j0 += gridDim.x * 32) {
     const int j = j0 + tx;
-    float ss = 0.f;
+    // G = F V holds column-wise even if rounding let |v_j| drift from 1:
+    // lambda_j = |g_j| / |v_j|, q_j = v_j / |v_j|.
+    float ss = 0.f, vv = 0.f;
     for (int i = ty; i < n; i += 8) {
       if (j < n) {
         const float g = mt.G[(int64_t)i * np + j];
+        const float v = mt.V[(int64_t)i * np + j];
         ss = fmaf(g, g, ss);
-        mt.Q[(int64_t)i * n + j] = mt.V[(int64_t)i * np + j];
+        vv = fmaf(v, v, vv);
       }
     }
     red[ty][tx] = ss;
+    redv[ty][tx] = vv;
     __syncthreads();
-    if (ty == 0 && j < n) {
-      float t = 0.f;
+    float tg = 0.f, tv = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t += red[k][tx];
-      mt.d[j] = sqrtf(t);
-    }
+    for (int k = 0; k < 8; ++k) { tg += red[k][tx]; tv += redv[k][tx]; }
+    const float inv_v = tv > 0.f ? 1.f / sqrtf(tv) : 0.f;
+    if (ty == 0 && j < n) mt.d[j] = sqrtf(tg) * inv_v;
+    for (int i = ty; i < n; i += 8)
+      if (j < n) {
+        const float q = mt.V[(int64_t)i * np + j] * inv_v;
+        mt.Q[(int64_t)i * mt.ldq + j] = q;
+        if (mt.QT) mt.QT[(int64_t)j * mt.ldq + i] = q;
+      }
     __syncthreads();
   }
 }
@@ -206,9 +217,11 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
   }
   const float tol_in = mode_block ? fminf(tol * 0.125f, 1e-6f) : 1e-7f;
 
+  int* pq = reinterpret_cast<int*>(cs + N);   // (p,q) of every pair of the current step
   for (int sweep = 0; sweep < max_inner; ++sweep) {
-    int rotated = 0;
+    int rotated_sweep = 0;
     for (int st = 0; st < N - 1; ++st) {
+      int rotated = 0;
       if (tid < N / 2) {
         int p, q;
         tournament(st, tid, N, p, q);
@@ -217,43 +230,44 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
         if (fabsf(apq) > tol_in * sqrtf(fabsf(app * aqq))) {
           const float tau = (aqq - app) / (2.f * apq);
           const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-          c = rsqrtf(1.f + t * t);
+          c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's bias makes column norms drift
           s = t * c;
           if (s != 0.f) rotated = 1;
         }
         cs[tid] = c;
         cs[N / 2 + tid] = s;
+        pq[tid] = p | (q << 16);
       }
-      __syncthreads();
-      // column rotation of M and W
+      // barrier + "did anybody rotate": a step without rotations is skipped entirely
+      if (!__syncthreads_or(rotated)) continue;
+      rotated_sweep = 1;
+      // M <- J^T M J on independent 2x2 blocks (pair a rows) x (pair b columns)
+      for (int idx = tid; idx < (N / 2) * (N / 2); idx += T) {
+        const int b = idx % (N / 2), a = idx / (N / 2);
+        const float ca = cs[a], sa = cs[N / 2 + a], cb = cs[b], sb = cs[N / 2 + b];
+        if (sa == 0.f && sb == 0.f) continue;
+        const int pa = pq[a] & 0xffff, qa = pq[a] >> 16, pb = pq[b] & 0xffff, qb = pq[b] >> 16;
+        const float m00 = M[pa][pb], m01 = M[pa][qb], m10 = M[qa][pb], m11 = M[qa][qb];
+        const float n00 = cb * m00 - sb * m01, n01 = sb * m00 + cb * m01;
+        const float n10 = cb * m10 - sb * m11, n11 = sb * m10 + cb * m11;
+        M[pa][pb] = ca * n00 - sa * n10;
+        M[pa][qb] = ca * n01 - sa * n11;
+        M[qa][pb] = sa * n00 + ca * n10;
+        M[qa][qb] = sa * n01 + ca * n11;
+      }
+      // W <- W J
       for (int idx = tid; idx < N * (N / 2); idx += T) {
         const int i = idx % N, k = idx / N;
         const float c = cs[k], s = cs[N / 2 + k];
         if (s == 0.f) continue;
-        int p, q;
-        tournament(st, k, N, p, q);
-        const float x = M[i][p], y = M[i][q];
-        M[i][p] = c * x - s * y;
-        M[i][q] = s * x + c * y;
+        const int p = pq[k] & 0xffff, q = pq[k] >> 16;
         const float u = W[i][p], v = W[i][q];
         W[i][p] = c * u - s * v;
         W[i][q] = s * u + c * v;
       }
       __syncthreads();
-      // row rotation of M
-      for (int idx = tid; idx < N * (N / 2); idx += T) {
-        const int j = idx % N, k = idx / N;
-        const float c = cs[k], s = cs[N / 2 + k];
-        if (s == 0.f) continue;
-        int p, q;
-        tournament(st, k, N, p, q);
-        const float x = M[p][j], y = M[q][j];
-        M[p][j] = c * x - s * y;
-        M[q][j] = s * x + c * y;
-      }
-      __syncthreads();
     }
-    if (!__syncthreads_or(rotated)) break;
+    if (!rotated_sweep) break;
   }
 
   if (mode_block) {
@@ -261,11 +275,20 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
     for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx / N][idx % N];
   } else {
     const int n = mt.n;
+    // M = W^T F W: rescale by the (rounding-drifted) column norms of W
+    for (int j = tid; j < N; j += T) {
+      float ww = 0.f;
+      for (int i = 0; i < N; ++i) ww = fmaf(W[i][j], W[i][j], ww);
+      cs[j] = ww > 0.f ? 1.f / sqrtf(ww) : 0.f;
+    }
+    __syncthreads();
     for (int idx = tid; idx < n * n; idx += T) {
       const int i = idx / n, j = idx % n;
-      mt.Q[idx] = W[i][j];
+      const float q = W[i][j] * cs[j];
+      mt.Q[(int64_t)i * mt.ldq + j] = q;
+      if (mt.QT) mt.QT[(int64_t)j * mt.ldq + i] = q;
     }
-    for (int j = tid; j < n; j += T) mt.d[j] = fmaxf(M[j][j], 0.f);
+    for (int j = tid; j < n; j += T) mt.d[j] = fmaxf(M[j][j] * cs[j] * cs[j], 0.f);
   }
 }
 
@@ -327,7 +350,8 @@ __global__ void __launch_bounds__(256) eigh_apply_kernel(EighMat* mats, const in
   }
 }
 
-__global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock, int round) {
+__global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock, int round, int* all_done) {
+  int pending = 0;
   for (int i = threadIdx.x; i < nblock; i += blockDim.x) {
     EighMat& mt = mats[block_list[i]];
     if (mt.done) continue;
@@ -336,14 +360,17 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
       if (__uint_as_float(mt.sweep_off) < mt.tol) mt.done = 1;
       mt.sweep_off = 0u;
     }
+    if (!mt.done) pending = 1;
   }
+  pending = __syncthreads_or(pending);
+  if (threadIdx.x == 0) *all_done = pending ? 0 : 1;
 }
 
 // --------------------------------------------------------------- host side
 struct EighPlan {
   std::vector<EighMat> mats;
   std::vector<int> pair_mat, block_list, d64_list, d128_list;
-  size_t off_mats, off_pair_mat, off_block, off_d64, off_d128, off_data, total;
+  size_t off_mats, off_pair_mat, off_block, off_d64, off_d128, off_flag, off_data, total;
   int total_pairs, max_nb, max_rows;
 };
 
@@ -375,6 +402,7 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
   pl.off_block = take(sizeof(int) * std::max<size_t>(1, pl.block_list.size()));
   pl.off_d64 = take(sizeof(int) * std::max<size_t>(1, pl.d64_list.size()));
   pl.off_d128 = take(sizeof(int) * std::max<size_t>(1, pl.d128_list.size()));
+  pl.off_flag = take(sizeof(int) * 4);
   pl.off_data = off;
   for (int i = 0; i < count; ++i) {
     EighMat& m = pl.mats[i];
@@ -406,7 +434,8 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
   cudaStream_t s = (cudaStream_t)stream;
   std::vector<int> ns(count);
   for (int i = 0; i < count; ++i) {
-    KFAC_CHECK_ARG(items[i].F && items[i].Q && items[i].d && items[i].n > 0, "eigh item");
+    KFAC_CHECK_ARG(items[i].F && items[i].Q && items[i].d && items[i].n > 0 &&
+                       (items[i].ldq == 0 || items[i].ldq >= items[i].n), "eigh item");
     ns[i] = items[i].n;
   }
   EighPlan pl;
@@ -415,11 +444,13 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     set_error("eigh: workspace too small (%zu < %zu)", ws_bytes, pl.total);
     return KFAC_ERR_WORKSPACE;
   }
-  if (max_sweeps <= 0) max_sweeps = 16;
+  if (max_sweeps <= 0) max_sweeps = 30;
+  const int inner_sweeps = 2;   // per block pair and round; the outer sweeps finish the job
   char* base = (char*)ws;
   for (int i = 0; i < count; ++i) {
     EighMat& m = pl.mats[i];
-    m.F = items[i].F; m.Q = items[i].Q; m.d = items[i].d;
+    m.F = items[i].F; m.Q = items[i].Q; m.QT = items[i].QT; m.d = items[i].d;
+    m.ldq = items[i].ldq > 0 ? items[i].ldq : items[i].n;
     m.tol = tol > 0.f ? tol : 1e-6f * sqrtf(fmaxf(1.f, (float)m.n / 16.f));
     if (m.mode == 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
@@ -444,8 +475,8 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     KFAC_CUDA(cudaMemcpyAsync(d_d128, pl.d128_list.data(), sizeof(int) * pl.d128_list.size(), cudaMemcpyHostToDevice, s));
   // the host vectors are pageable: cudaMemcpyAsync stages them before returning.
 
-  const size_t smem64 = (2 * 64 * 65 + 64) * sizeof(float);
-  const size_t smem128 = (2 * 128 * 129 + 128) * sizeof(float);
+  const size_t smem64 = (2 * 64 * 65 + 64 + 32) * sizeof(float);
+  const size_t smem128 = (2 * 128 * 129 + 128 + 64) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     KFAC_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
@@ -464,16 +495,36 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
   if (nblock > 0) {
     eigh_init_kernel<<<dim3(256, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();
-    const int rounds = max_sweeps * (pl.max_nb - 1);
+    const int rps = pl.max_nb - 1;                 // rounds per sweep of the largest matrix
     const int chunks = ceil_div(pl.max_rows, GR);
-    for (int r = 0; r < rounds; ++r) {
-      eigh_gram_kernel<<<dim3(pl.total_pairs, chunks), 256, 0, s>>>(d_mats, d_pair_mat, r);
-      jacobi_smem_kernel<64><<<pl.total_pairs, 256, smem64, s>>>(d_mats, d_pair_mat, 1, 8);
-      eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
-      eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r);
+    int* d_flag = (int*)(base + pl.off_flag);
+    // Early exit without draining the GPU: the host enqueues sweep s+1, then waits
+    // for the "all matrices converged" flag of sweep s (pinned read-back + event).
+    static int* h_flag = nullptr;
+    static cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!h_flag) {
+      KFAC_CUDA(cudaMallocHost(&h_flag, 2 * sizeof(int)));
+      KFAC_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+      KFAC_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     }
-    count_launch(4 * rounds - 1);
-    KFAC_LAUNCH_CHECK();
+    for (int sw = 0; sw < max_sweeps; ++sw) {
+      for (int rr = 0; rr < rps; ++rr) {
+        const int r = sw * rps + rr;
+        eigh_gram_kernel<<<dim3(pl.total_pairs, chunks), 256, 0, s>>>(d_mats, d_pair_mat, r);
+        jacobi_smem_kernel<64><<<pl.total_pairs, 256, smem64, s>>>(d_mats, d_pair_mat, 1, inner_sweeps);
+        eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
+        eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r, d_flag);
+      }
+      count_launch(4 * rps - 1);
+      KFAC_LAUNCH_CHECK();
+      h_flag[sw & 1] = 0;
+      KFAC_CUDA(cudaMemcpyAsync(&h_flag[sw & 1], d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+      KFAC_CUDA(cudaEventRecord(ev[sw & 1], s));
+      if (sw >= 1) {
+        KFAC_CUDA(cudaEventSynchronize(ev[(sw - 1) & 1]));
+        if (h_flag[(sw - 1) & 1]) break;
+      }
+    }
     eigh_final_kernel<<<dim3(64, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();
   }

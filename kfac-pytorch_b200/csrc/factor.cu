@@ -173,11 +173,13 @@ __global__ void ema_kernel(EmaBatch eb) {
   }
 }
 
-__global__ void dgda_kernel(const float* dg, const float* da, int g, int a, float damping, float* out) {
-  const int64_t total = (int64_t)g * a;
+__global__ void dgda_kernel(const float* dg, const float* da, int g, int a, float damping, float* out, int ldo) {
+  const int64_t total = (int64_t)g * ldo;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x)
-    out[idx] = 1.f / (dg[idx / a] * da[idx % a] + damping);
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % ldo);
+    out[idx] = j < a ? 1.f / (dg[idx / ldo] * da[j] + damping) : 0.f;
+  }
 }
 
 __global__ void triu_pack_kernel(const float* F, int n, float* packed) {
@@ -300,9 +302,9 @@ extern "C" int kfac_factor_ema(const kfac_ema_item* items, int count, float alph
 }
 
 extern "C" int kfac_dgda(const float* dg, const float* da, int g, int a, float damping, float* out,
-                         void* stream) {
-  KFAC_CHECK_ARG(dg && da && out && g > 0 && a > 0, "dgda args");
-  dgda_kernel<<<grid_for((int64_t)g * a), 256, 0, (cudaStream_t)stream>>>(dg, da, g, a, damping, out);
+                         int ld_out, void* stream) {
+  KFAC_CHECK_ARG(dg && da && out && g > 0 && a > 0 && ld_out >= a, "dgda args");
+  dgda_kernel<<<grid_for((int64_t)g * ld_out), 256, 0, (cudaStream_t)stream>>>(dg, da, g, a, damping, out, ld_out);
   KFAC_LAUNCH_CHECK();
   return KFAC_OK;
 }

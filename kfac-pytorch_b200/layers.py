@@ -204,7 +204,9 @@ class KFACLayer:
         self._has_a = self._has_g = False       # running average exists
         self._a_count = self._g_count = 0       # accumulated micro-batches
         self._a_pending = self._g_pending = False
-        self._inv = {}                          # name -> view (qa, qg, da, dg, dgda, a_inv, g_inv)
+        self._inv = {}                          # name -> storage (rows x ld4(cols)) of qa, qg, da, dg, dgda, a_inv, g_inv
+        self._inv_cols = {}                     # name -> logical column count
+        self._p_store = None
         self._inv_ready = set()
         self._p_view = None
         self._grad_ready = False
@@ -222,7 +224,10 @@ class KFACLayer:
         return self._g_view if self._has_g else None
 
     def _inv_get(self, key):
-        return self._inv.get(key) if key in self._inv_ready else None
+        if key not in self._inv_ready:
+            return None
+        t = self._inv[key]
+        return t[:, :self._inv_cols[key]] if t.dim() == 2 else t
 
     qa = property(lambda self: self._inv_get('qa'))
     qg = property(lambda self: self._inv_get('qg'))

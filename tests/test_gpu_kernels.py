@@ -176,11 +176,14 @@ def run_eigh(lib, dev, mats):
     for i, F in enumerate(mats):
         n = F.shape[0]
         Fd = F.to(dev).contiguous()
-        Q = torch.empty(n, n, device=dev)
+        ld = _cabi.ld4(n)
+        Qs = torch.zeros(n, ld, device=dev)
+        QTs = torch.zeros(n, ld, device=dev)
         d = torch.empty(n, device=dev)
-        items[i] = _cabi.EighItem(Fd.data_ptr(), Q.data_ptr(), d.data_ptr(), n)
+        items[i] = _cabi.EighItem(Fd.data_ptr(), Qs.data_ptr(), QTs.data_ptr() if i % 2 == 0 else None,
+                                  d.data_ptr(), n, ld)
         ns[i] = n
-        outs.append((Fd, Q, d))
+        outs.append((Fd, Qs[:, :n], d, QTs[:, :n] if i % 2 == 0 else None))
     need = lib.kfac_eigh_workspace_bytes(ns, len(mats))
     ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
     rc = lib.kfac_eigh_batched(items, len(mats), ws.data_ptr(), need, 0, 0.0, S())
@@ -212,14 +215,16 @@ def test_eigh_batched_sizes(lib, dev, kind):
     mats = [make_psd(n, kind, 17 * n + 3) for n in sizes]
     outs = run_eigh(lib, dev, mats)
     worst = 0.0
-    for F, Q, d in outs:
+    for F, Q, d, QT in outs:
         worst = max(worst, check_eigh(F, Q, d))
+        if QT is not None:
+            assert torch.equal(QT, Q.t())
     print(kind, 'worst functional error', worst)
 
 
 def test_eigh_large(lib, dev):
     mats = [make_psd(1152, 'cov', 5), make_psd(1024, 'geo', 6)]
-    for F, Q, d in run_eigh(lib, dev, mats):
+    for F, Q, d, _ in run_eigh(lib, dev, mats):
         check_eigh(F, Q, d)
 
 
@@ -228,21 +233,24 @@ def test_dgda_and_inverse(lib, dev):
     torch.manual_seed(3)
     dg, da = torch.rand(37), torch.rand(130)
     out = torch.empty(37, 130, device=dev)
-    assert lib.kfac_dgda(dg.to(dev).data_ptr(), da.to(dev).data_ptr(), 37, 130, 0.003, out.data_ptr(), S()) == 0
+    out = torch.empty(37, 132, device=dev)
+    assert lib.kfac_dgda(dg.to(dev).data_ptr(), da.to(dev).data_ptr(), 37, 130, 0.003, out.data_ptr(), 132, S()) == 0
     torch.cuda.synchronize()
-    assert rel_fro(out, O.eigen_dgda(dg, da, 0.003)) < 1e-6
+    assert rel_fro(out[:, :130], O.eigen_dgda(dg, da, 0.003)) < 1e-6
     for n in (10, 64, 200):
         F = make_psd(n, 'cov', n)
-        (Fd, Q, d), = run_eigh(lib, dev, [F])
-        inv = torch.empty(n, n, device=dev)
-        ws = torch.empty(n * n, device=dev)
-        assert lib.kfac_inverse_from_eigh(Q.data_ptr(), d.data_ptr(), n, 0.01, inv.data_ptr(), ws.data_ptr(),
-                                          n * n * 4, S()) == 0
+        (Fd, Q, d, _), = run_eigh(lib, dev, [F])
+        from kfac_b200 import _cabi
+        ld = _cabi.ld4(n)
+        inv = torch.empty(n, ld, device=dev)
+        ws = torch.empty(n * ld, device=dev)
+        assert lib.kfac_inverse_from_eigh(Q.data_ptr(), ld, d.data_ptr(), n, 0.01, inv.data_ptr(), ld,
+                                          ws.data_ptr(), n * ld * 4, S()) == 0
         torch.cuda.synchronize()
-        assert rel_fro(inv, O.damped_inverse(F, 0.01)) < 1e-3
+        assert rel_fro(inv[:, :n], O.damped_inverse(F, 0.01)) < 1e-3
 
 
-@pytest.mark.parametrize('g,a,bias,method', [(20, 10, 0, 'eigen'), (10, 21, 1, 'eigen'), (64, 577, 1, 'eigen'),
+@pytest.mark.parametrize('g,a,bias,method', [(20, 10, 0, 'eigen'), (10, 21, 1, 'eigen'), (64, 577, 1, 'eigen'), (256, 1153, 1, 'eigen'), (512, 1024, 0, 'eigen'), (384, 640, 0, 'inverse'),
                                               (130, 65, 0, 'eigen_noprediv'), (16, 145, 1, 'inverse'), (200, 300, 0, 'inverse')])
 def test_precondition_and_update(lib, dev, g, a, bias, method):
     from kfac_b200 import _cabi
@@ -257,23 +265,32 @@ def test_precondition_and_update(lib, dev, g, a, bias, method):
     damping = 0.003
     dgda = O.eigen_dgda(dg, da, damping)
     t = lambda x: x.to(dev).contiguous() if x is not None else None  # noqa: E731
+
+    def pad(x):   # (rows, cols) -> storage with ld4(cols)
+        out = torch.zeros(x.shape[0], _cabi.ld4(x.shape[1]), device=dev)
+        out[:, :x.shape[1]] = x.to(dev)
+        return out
     wd, bd = t(wgrad), t(bgrad)
-    P = torch.empty(g, a, device=dev)
-    keep = dict(qa=t(qa), qg=t(qg), dgda=t(dgda), da=t(da), dg=t(dg),
-                a_inv=t(O.damped_inverse(A, damping)), g_inv=t(O.damped_inverse(G, damping)))
+    lda_, ldg_ = _cabi.ld4(a), _cabi.ld4(g)
+    Ps = torch.zeros(g, lda_, device=dev)
+    P = Ps[:, :a]
+    a_inv_ref, g_inv_ref = O.damped_inverse(A, damping), O.damped_inverse(G, damping)
+    keep = dict(qa=pad(qa), qaT=pad(qa.t()), qg=pad(qg), qgT=pad(qg.t()), dgda=pad(dgda), da=t(da), dg=t(dg),
+                a_inv=pad(a_inv_ref), g_inv=pad(g_inv_ref))
     p = lambda k, use: keep[k].data_ptr() if use else None  # noqa: E731
     e, pre, inv = method.startswith('eigen'), method == 'eigen', method == 'inverse'
     items = (_cabi.PrecondItem * 1)()
     items[0] = _cabi.PrecondItem(wd.data_ptr(), bd.data_ptr() if bias else None, 0, g, a,
-                                 p('qa', e), p('qg', e), p('dgda', pre), p('da', e and not pre), p('dg', e and not pre),
-                                 p('a_inv', inv), p('g_inv', inv), P.data_ptr())
+                                 p('qa', e), p('qaT', e), p('qg', e), p('qgT', e), p('dgda', pre),
+                                 p('da', e and not pre), p('dg', e and not pre),
+                                 p('a_inv', inv), p('g_inv', inv), lda_, ldg_, lda_, Ps.data_ptr(), lda_)
     need = lib.kfac_precondition_workspace_bytes(items, 1)
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     rc = lib.kfac_precondition(items, 1, 2 if inv else 1, damping, ws.data_ptr(), need, S())
     assert rc == 0, lib.kfac_last_error()
     torch.cuda.synchronize()
     if inv:
-        ref = O.precondition_inverse(grad, keep['a_inv'].cpu(), keep['g_inv'].cpu())
+        ref = O.precondition_inverse(grad, a_inv_ref, g_inv_ref)
     elif pre:
         ref = O.precondition_eigen(grad, qa, qg, dgda=dgda)
     else:
@@ -282,7 +299,7 @@ def test_precondition_and_update(lib, dev, g, a, bias, method):
 
     # kl-clip scale + in-place write back
     gi = (_cabi.GradItem * 1)()
-    gi[0] = _cabi.GradItem(P.data_ptr(), wd.data_ptr(), bd.data_ptr() if bias else None, 0, g, a)
+    gi[0] = _cabi.GradItem(Ps.data_ptr(), wd.data_ptr(), bd.data_ptr() if bias else None, 0, g, a, lda_)
     vg = torch.zeros(1, dtype=torch.float64, device=dev)
     nu = torch.zeros(1, device=dev)
     assert lib.kfac_grad_scale(gi, 1, 0.001, 0.1, vg.data_ptr(), nu.data_ptr(), S()) == 0
@@ -299,14 +316,15 @@ def test_not_ready_maps_to_runtime_error(lib, dev):
     w = torch.randn(4, 4, device=dev)
     P = torch.empty(4, 4, device=dev)
     items = (_cabi.PrecondItem * 1)()
-    items[0] = _cabi.PrecondItem(w.data_ptr(), None, 0, 4, 4, None, None, None, None, None, None, None, P.data_ptr())
+    items[0] = _cabi.PrecondItem(w.data_ptr(), None, 0, 4, 4, None, None, None, None, None, None, None, None, None,
+                                 4, 4, 4, P.data_ptr(), 4)
     ws = torch.empty(4096, dtype=torch.uint8, device=dev)
     rc = lib.kfac_precondition(items, 1, 1, 0.1, ws.data_ptr(), 4096, S())
     assert rc == _cabi.KFAC_ERR_NOT_READY
     with pytest.raises(RuntimeError):
         _cabi.check(rc)
     with pytest.raises(ValueError):
-        _cabi.check(lib.kfac_dgda(None, None, 0, 0, 0.1, None, S()))
+        _cabi.check(lib.kfac_dgda(None, None, 0, 0, 0.1, None, 0, S()))
 
 
 @pytest.mark.parametrize('n', [1, 2, 5, 64, 257])

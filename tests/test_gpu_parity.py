@@ -11,6 +11,12 @@ from conftest import rel_fro, replay
 
 pytestmark = pytest.mark.gpu
 
+# compare like with like: the CPU oracle's forward/backward is fp32, so keep the
+# GPU model's convolutions/matmuls out of TF32 (the K-FAC path itself never uses it
+# unsplit).
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 NAMES = ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
          'conv_eigen', 'conv_inverse', 'conv_accum']
 
