@@ -107,7 +107,7 @@ typedef struct kfac_eigh_item {
   int ldq;        /* 0 -> n.  Multiples of 4 let the tensor-core GEMMs consume Q directly */
 } kfac_eigh_item;
 size_t kfac_eigh_workspace_bytes(const int* n, int count);
-/* max_sweeps <= 0 -> default (16); tol <= 0 -> automatic (scaled with sqrt(n)) */
+/* max_sweeps <= 0 -> default (30); tol <= 0 -> automatic (scaled with sqrt(n)) */
 int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* ws,
                       size_t ws_bytes, int max_sweeps, float tol, void* stream);
 

@@ -105,5 +105,6 @@ struct TcGemmArgs {
 };
 bool tc_gemm_supported(const TcGemmArgs& a);
 int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream);
+int tc_num_sms();
 
 }  // namespace kfac

@@ -15,6 +15,7 @@
 // per phase for the whole batch); per-matrix `done` flags computed on the
 // device make converged matrices drop out without a host sync.
 #include "common.cuh"
+#include "tc_pipeline.cuh"
 
 #include <vector>
 
@@ -24,13 +25,18 @@ constexpr int JB = 32;        // block width
 constexpr int JP = 2 * JB;    // pair width
 constexpr int GR = 256;       // rows of G handled per CTA in gram/apply
 
-struct EighMat {
+constexpr int TC_MIN_N = 384; // block matrices at least this large use the tcgen05 Gram/apply kernels
+
+struct alignas(64) EighMat {
+  CUtensorMap tmG, tmGt, tmV, tmW;   // mode 3 only (TMA views of G, G^T, V and the W^T pair buffers)
   const float* F; float* Q; float* QT; float* d;
   int ldq;
   float* G; float* V;          // np x np
-  float* M; float* W;          // pairs x JP x JP
+  float* Gt;                   // mode 3: transposed copy of G (K-major operand of the Gram)
+  float* M; float* W;          // pairs x JP x JP   (mode 3: W holds W^T)
   int* pair_skip;              // pairs
   int n, np, nb, pair_base, mode;
+  int gram_base;               // mode 3: first Gram item (two pairs per 128-row MMA tile)
   float tol;
   unsigned int sweep_off;      // float bits, atomicMax
   int done;
@@ -61,7 +67,9 @@ __global__ void eigh_init_kernel(EighMat* mats, const int* block_list) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx / np), j = (int)(idx % np);
-    mt.G[idx] = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
+    const float f = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
+    mt.G[idx] = f;
+    if (mt.mode == 3) mt.Gt[idx] = (i < n && j < n) ? mt.F[(int64_t)j * n + i] : 0.f;
     mt.V[idx] = (i == j) ? 1.f : 0.f;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; }
@@ -272,7 +280,8 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
 
   if (mode_block) {
     float* Wg = mt.W + (int64_t)local * JP * JP;
-    for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx / N][idx % N];
+    if (mt.mode == 3) { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx % N][idx / N]; }   // W^T
+    else { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx / N][idx % N]; }
   } else {
     const int n = mt.n;
     // M = W^T F W: rescale by the (rounding-drifted) column norms of W
@@ -366,24 +375,115 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
   if (threadIdx.x == 0) *all_done = pending ? 0 : 1;
 }
 
+
+// ------------------------------------------------ tcgen05 Gram / apply (mode 3)
+// Gram: two block pairs share one 128-row MMA tile.  A = B = rows {I1,J1,I2,J2} of
+// G^T (K-major, K = row index of G), D[128x128] = A A^T; the two diagonal 64x64
+// quadrants are the pair Grams (the off-diagonal quadrants are discarded).
+struct GramParams { EighMat* mats; const int* item_mat; int ksplits; int round; };
+struct GramPolicy {
+  using Params = GramParams;
+  struct Item { EighMat* mt; int p0, I1, J1, I2, J2, kb0, kb1; };
+  static constexpr int BN = 128;
+  static constexpr bool B_IS_A = true;
+  static constexpr uint32_t TX_BYTES = tc::PTILE;
+  __device__ static bool decode(const Params& p, int w, Item& it) {
+    const int gi = w / p.ksplits, sp = w % p.ksplits;
+    EighMat* mt = &p.mats[p.item_mat[gi]];
+    if (mt->done) return false;
+    it.mt = mt;
+    it.p0 = 2 * (gi - mt->gram_base);
+    const int r = p.round % (mt->nb - 1);
+    tournament(r, it.p0, mt->nb, it.I1, it.J1);
+    tournament(r, it.p0 + 1, mt->nb, it.I2, it.J2);
+    const int kb_total = (mt->n + 31) / 32;
+    const int per = (kb_total + p.ksplits - 1) / p.ksplits;
+    it.kb0 = sp * per; it.kb1 = min(kb_total, it.kb0 + per);
+    return it.kb1 > it.kb0;
+  }
+  __device__ static int num_kb(const Params&, const Item& it) { return it.kb1 - it.kb0; }
+  __device__ static void load(const Params&, const Item& it, int kbi, uint8_t* a, uint8_t*, uint64_t* bar) {
+    const int kc = (it.kb0 + kbi) * 32;
+    tc::tma_load_3d(a, &it.mt->tmGt, bar, kc, it.I1 * JB, 0);
+    tc::tma_load_3d(a + 4096, &it.mt->tmGt, bar, kc, it.J1 * JB, 0);
+    tc::tma_load_3d(a + 8192, &it.mt->tmGt, bar, kc, it.I2 * JB, 0);
+    tc::tma_load_3d(a + 12288, &it.mt->tmGt, bar, kc, it.J2 * JB, 0);
+  }
+  __device__ static void store(const Params&, const Item& it, int row, int col0, float (&v)[32]) {
+    float* M;
+    if (row < 64) { if (col0 >= 64) return; M = it.mt->M + (int64_t)it.p0 * JP * JP + row * JP + col0; }
+    else { if (col0 < 64) return; M = it.mt->M + (int64_t)(it.p0 + 1) * JP * JP + (row - 64) * JP + (col0 - 64); }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) atomicAdd(M + j, v[j]);
+  }
+};
+
+// Apply: X[rows, I u J] <- X[rows, I u J] W for X in {G, V}; G also refreshes G^T.
+struct ApplyParams { EighMat* mats; const int* pair_mat; int max_tiles; int round; };
+struct ApplyPolicy {
+  using Params = ApplyParams;
+  struct Item { EighMat* mt; int local, I, J, m0, which; };
+  static constexpr int BN = 64;
+  static constexpr bool B_IS_A = false;
+  static constexpr uint32_t TX_BYTES = tc::PTILE + 64 * 32 * 4;
+  __device__ static bool decode(const Params& p, int w, Item& it) {
+    it.which = w & 1;
+    const int t = (w >> 1) % p.max_tiles, pr = (w >> 1) / p.max_tiles;
+    EighMat* mt = &p.mats[p.pair_mat[pr]];
+    if (mt->done) return false;
+    it.mt = mt;
+    it.local = pr - mt->pair_base;
+    if (mt->pair_skip[it.local]) return false;
+    it.m0 = t * 128;
+    if (it.m0 >= mt->n) return false;
+    tournament(p.round % (mt->nb - 1), it.local, mt->nb, it.I, it.J);
+    return true;
+  }
+  __device__ static int num_kb(const Params&, const Item&) { return 2; }
+  __device__ static void load(const Params&, const Item& it, int kbi, uint8_t* a, uint8_t* b, uint64_t* bar) {
+    tc::tma_load_3d(a, it.which ? &it.mt->tmV : &it.mt->tmG, bar, (kbi == 0 ? it.I : it.J) * JB, it.m0, 0);
+    tc::tma_load_3d(b, &it.mt->tmW, bar, kbi * 32, 0, it.local);
+  }
+  __device__ static void store(const Params&, const Item& it, int row, int col0, float (&v)[32]) {
+    const int r = it.m0 + row;
+    if (r >= it.mt->n) return;
+    const int np = it.mt->np, cb = (col0 == 0 ? it.I : it.J) * JB;
+    float* X = (it.which ? it.mt->V : it.mt->G) + (int64_t)r * np + cb;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(X + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    if (!it.which) {
+      float* T = it.mt->Gt + (int64_t)cb * np + r;   // lanes hold consecutive rows r: coalesced columns of G^T
+#pragma unroll
+      for (int j = 0; j < 32; ++j) T[(int64_t)j * np] = v[j];
+    }
+  }
+};
+
+int make_tmap_3d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                 uint64_t stride2_bytes, uint32_t box_rows);
+
 // --------------------------------------------------------------- host side
 struct EighPlan {
   std::vector<EighMat> mats;
   std::vector<int> pair_mat, block_list, d64_list, d128_list;
+  std::vector<int> tc_pair_mat, tc_gram_mat, simt_list;
   size_t off_mats, off_pair_mat, off_block, off_d64, off_d128, off_flag, off_data, total;
+  size_t off_tc_pair, off_tc_gram, off_simt;
   int total_pairs, max_nb, max_rows;
+  int tc_pairs, tc_gram_items, tc_max_rows, simt_max_rows;
 };
 
 static void build_plan(const int* n, int count, EighPlan& pl) {
   pl.mats.resize(count);
   pl.total_pairs = 0; pl.max_nb = 0; pl.max_rows = 0;
+  pl.tc_pairs = 0; pl.tc_gram_items = 0; pl.tc_max_rows = 0; pl.simt_max_rows = 0;
   for (int i = 0; i < count; ++i) {
     EighMat& m = pl.mats[i];
     m = EighMat{};
     m.n = n[i];
     if (n[i] <= 64) { m.mode = 0; pl.d64_list.push_back(i); }
     else if (n[i] <= 128) { m.mode = 1; pl.d128_list.push_back(i); }
-    else {
+    else if (n[i] < TC_MIN_N) {
       m.mode = 2;
       m.np = (n[i] + JP - 1) / JP * JP;
       m.nb = m.np / JB;
@@ -392,6 +492,22 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
       pl.total_pairs += m.nb / 2;
       pl.max_nb = std::max(pl.max_nb, m.nb);
       pl.max_rows = std::max(pl.max_rows, n[i]);
+      pl.simt_max_rows = std::max(pl.simt_max_rows, n[i]);
+      pl.block_list.push_back(i);
+      pl.simt_list.push_back(i);
+    } else {
+      m.mode = 3;
+      m.np = (n[i] + 127) / 128 * 128;      // 128-row MMA tiles; nb % 4 == 0 -> pairs come in twos
+      m.nb = m.np / JB;
+      m.pair_base = pl.tc_pairs;
+      m.gram_base = pl.tc_gram_items;
+      for (int k = 0; k < m.nb / 2; ++k) pl.tc_pair_mat.push_back(i);
+      for (int k = 0; k < m.nb / 4; ++k) pl.tc_gram_mat.push_back(i);
+      pl.tc_pairs += m.nb / 2;
+      pl.tc_gram_items += m.nb / 4;
+      pl.max_nb = std::max(pl.max_nb, m.nb);
+      pl.max_rows = std::max(pl.max_rows, n[i]);
+      pl.tc_max_rows = std::max(pl.tc_max_rows, n[i]);
       pl.block_list.push_back(i);
     }
   }
@@ -403,13 +519,17 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
   pl.off_d64 = take(sizeof(int) * std::max<size_t>(1, pl.d64_list.size()));
   pl.off_d128 = take(sizeof(int) * std::max<size_t>(1, pl.d128_list.size()));
   pl.off_flag = take(sizeof(int) * 4);
+  pl.off_tc_pair = take(sizeof(int) * std::max<size_t>(1, pl.tc_pair_mat.size()));
+  pl.off_tc_gram = take(sizeof(int) * std::max<size_t>(1, pl.tc_gram_mat.size()));
+  pl.off_simt = take(sizeof(int) * std::max<size_t>(1, pl.simt_list.size()));
   pl.off_data = off;
   for (int i = 0; i < count; ++i) {
     EighMat& m = pl.mats[i];
-    if (m.mode != 2) continue;
+    if (m.mode < 2) continue;
     const size_t sq = (size_t)m.np * m.np * sizeof(float);
     const size_t pb = (size_t)(m.nb / 2) * JP * JP * sizeof(float);
     m.G = (float*)take(sq); m.V = (float*)take(sq);      // offsets, rebased later
+    if (m.mode == 3) m.Gt = (float*)take(sq);
     m.M = (float*)take(pb); m.W = (float*)take(pb);
     m.pair_skip = (int*)take(sizeof(int) * (m.nb / 2));
   }
@@ -452,11 +572,24 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     m.F = items[i].F; m.Q = items[i].Q; m.QT = items[i].QT; m.d = items[i].d;
     m.ldq = items[i].ldq > 0 ? items[i].ldq : items[i].n;
     m.tol = tol > 0.f ? tol : 1e-6f * sqrtf(fmaxf(1.f, (float)m.n / 16.f));
-    if (m.mode == 2) {
+    if (m.mode >= 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
+      if (m.mode == 3) {
+        m.Gt = (float*)(base + (size_t)m.Gt);
+        const uint64_t np = m.np, rowb = np * 4;
+        int rc;
+        // G / V: 128-row x 32-column boxes; G^T: 32-row boxes; W^T pair buffers as {k, j, pair}
+        if ((rc = make_tmap_3d(&m.tmG, m.G, np, np, 1, rowb, rowb * np, 128))) return rc;
+        if ((rc = make_tmap_3d(&m.tmV, m.V, np, np, 1, rowb, rowb * np, 128))) return rc;
+        if ((rc = make_tmap_3d(&m.tmGt, m.Gt, np, np, 1, rowb, rowb * np, 32))) return rc;
+      }
       m.M = (float*)(base + (size_t)m.M); m.W = (float*)(base + (size_t)m.W);
       m.pair_skip = (int*)(base + (size_t)m.pair_skip);
       KFAC_CUDA(cudaMemsetAsync(m.M, 0, (size_t)(m.nb / 2) * JP * JP * sizeof(float), s));
+      if (m.mode == 3) {
+        int rc;
+        if ((rc = make_tmap_3d(&m.tmW, m.W, JP, JP, m.nb / 2, JP * 4, JP * JP * 4, 64))) return rc;
+      }
     }
   }
   EighMat* d_mats = (EighMat*)(base + pl.off_mats);
@@ -473,6 +606,13 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     KFAC_CUDA(cudaMemcpyAsync(d_d64, pl.d64_list.data(), sizeof(int) * pl.d64_list.size(), cudaMemcpyHostToDevice, s));
   if (!pl.d128_list.empty())
     KFAC_CUDA(cudaMemcpyAsync(d_d128, pl.d128_list.data(), sizeof(int) * pl.d128_list.size(), cudaMemcpyHostToDevice, s));
+  int* d_tc_pair = (int*)(base + pl.off_tc_pair);
+  int* d_tc_gram = (int*)(base + pl.off_tc_gram);
+  if (!pl.tc_pair_mat.empty()) {
+    KFAC_CUDA(cudaMemcpyAsync(d_tc_pair, pl.tc_pair_mat.data(), sizeof(int) * pl.tc_pair_mat.size(), cudaMemcpyHostToDevice, s));
+    KFAC_CUDA(cudaMemcpyAsync(d_tc_gram, pl.tc_gram_mat.data(), sizeof(int) * pl.tc_gram_mat.size(), cudaMemcpyHostToDevice, s));
+  }
+
   // the host vectors are pageable: cudaMemcpyAsync stages them before returning.
 
   const size_t smem64 = (2 * 64 * 65 + 64 + 32) * sizeof(float);
@@ -496,7 +636,24 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     eigh_init_kernel<<<dim3(256, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();
     const int rps = pl.max_nb - 1;                 // rounds per sweep of the largest matrix
-    const int chunks = ceil_div(pl.max_rows, GR);
+    const int chunks = ceil_div(std::max(1, pl.simt_max_rows), GR);
+    // tcgen05 class launch geometry
+    const int sms = tc_num_sms();
+    static bool tc_attr = false;
+    if (!tc_attr && pl.tc_pairs > 0) {
+      KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
+      KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<ApplyPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
+      tc_attr = true;
+    }
+    GramParams gp{d_mats, d_tc_gram, 1, 0};
+    ApplyParams ap{d_mats, d_tc_pair, std::max(1, ceil_div(std::max(1, pl.tc_max_rows), 128)), 0};
+    int gram_total = 0, apply_total = 0;
+    if (pl.tc_pairs > 0) {
+      const int kb_max = ceil_div(pl.tc_max_rows, 32);
+      gp.ksplits = std::max(1, std::min(ceil_div(2 * sms, pl.tc_gram_items), std::max(1, kb_max / 4)));
+      gram_total = pl.tc_gram_items * gp.ksplits;
+      apply_total = pl.tc_pairs * ap.max_tiles * 2;
+    }
     int* d_flag = (int*)(base + pl.off_flag);
     // Early exit without draining the GPU: the host enqueues sweep s+1, then waits
     // for the "all matrices converged" flag of sweep s (pinned read-back + event).
@@ -510,12 +667,21 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     for (int sw = 0; sw < max_sweeps; ++sw) {
       for (int rr = 0; rr < rps; ++rr) {
         const int r = sw * rps + rr;
-        eigh_gram_kernel<<<dim3(pl.total_pairs, chunks), 256, 0, s>>>(d_mats, d_pair_mat, r);
-        jacobi_smem_kernel<64><<<pl.total_pairs, 256, smem64, s>>>(d_mats, d_pair_mat, 1, inner_sweeps);
-        eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
+        if (pl.total_pairs > 0) {
+          eigh_gram_kernel<<<dim3(pl.total_pairs, chunks), 256, 0, s>>>(d_mats, d_pair_mat, r);
+          jacobi_smem_kernel<64><<<pl.total_pairs, 256, smem64, s>>>(d_mats, d_pair_mat, 1, inner_sweeps);
+          eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
+          count_launch(3);
+        }
+        if (pl.tc_pairs > 0) {
+          gp.round = r; ap.round = r;
+          tc::pipeline_kernel<GramPolicy><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
+          jacobi_smem_kernel<64><<<pl.tc_pairs, 256, smem64, s>>>(d_mats, d_tc_pair, 1, inner_sweeps);
+          tc::pipeline_kernel<ApplyPolicy><<<std::min(apply_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(ap, apply_total);
+          count_launch(3);
+        }
         eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r, d_flag);
       }
-      count_launch(4 * rps - 1);
       KFAC_LAUNCH_CHECK();
       h_flag[sw & 1] = 0;
       KFAC_CUDA(cudaMemcpyAsync(&h_flag[sw & 1], d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -11,17 +11,14 @@
 // 3 smem stages x {A_hi, B_hi, A_lo, B_lo} x 16 KB = 192 KB; 2 TMEM accumulators
 // (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
-#include "tc_common.cuh"
+#include "tc_pipeline.cuh"
 
 namespace kfac {
 
-constexpr int TBM = 128, TBN = 128, TBK = 32, TSTAGES = 3;
-constexpr int TILE_BYTES = TBM * TBK * 4;     // 16 KB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // 64 KB
-constexpr int TC_THREADS = 320;
-constexpr size_t TC_SMEM = (size_t)TSTAGES * STAGE_BYTES + 1024 + 256;
+constexpr int TBM = 128, TBN = 128, TBK = 32;
 
 struct TcParams {
+  CUtensorMap tmA, tmB;
   float* D; int64_t ldd;
   int M, N, K, kbatch;
   int tiles_m, tiles_n, splits, upper_only, atomic;
@@ -29,186 +26,68 @@ struct TcParams {
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
 };
 
-struct WorkItem { int m0, n0, kb0, kb1, diag; };
+struct GemmPolicy {
+  using Params = TcParams;
+  struct Item { int m0, n0, kb0, kb1, diag; };
+  static constexpr int BN = TBN;
+  static constexpr bool B_IS_A = false;
+  static constexpr uint32_t TX_BYTES = 2 * tc::PTILE;
 
-__device__ __forceinline__ WorkItem decode_work(const TcParams& p, int w) {
-  WorkItem it;
-  const int tile = w / p.splits, sp = w % p.splits;
-  int tm, tn;
-  if (p.upper_only) {
-    int t = tile; tm = 0;
-    while (t >= p.tiles_n - tm) { t -= p.tiles_n - tm; ++tm; }
-    tn = tm + t;
-  } else { tm = tile / p.tiles_n; tn = tile % p.tiles_n; }
-  it.m0 = tm * TBM; it.n0 = tn * TBN; it.diag = (tm == tn);
-  const int kblocks = (p.K + TBK - 1) / TBK;
-  const int kb_total = kblocks * p.kbatch;
-  const int per = (kb_total + p.splits - 1) / p.splits;
-  it.kb0 = sp * per; it.kb1 = min(kb_total, it.kb0 + per);
-  return it;
-}
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p,
-               int total_work) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)TSTAGES * STAGE_BYTES);
-  uint64_t* full = bars;                   // [TSTAGES]  TMA landed
-  uint64_t* conv = bars + TSTAGES;         // [TSTAGES]  lo tiles written
-  uint64_t* empty = bars + 2 * TSTAGES;    // [TSTAGES]  MMAs retired
-  uint64_t* tfull = bars + 3 * TSTAGES;    // [2] accumulator ready
-  uint64_t* tempty = tfull + 2;            // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = (p.K + TBK - 1) / TBK;
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmA);
-    tc::prefetch_tmap(&tmB);
-    for (int s = 0; s < TSTAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&conv[s], 4); tc::mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 4); }
-    tc::fence_barrier_init();
+  __device__ static bool decode(const Params& p, int w, Item& it) {
+    const int tile = w / p.splits, sp = w % p.splits;
+    int tm, tn;
+    if (p.upper_only) {
+      int t = tile; tm = 0;
+      while (t >= p.tiles_n - tm) { t -= p.tiles_n - tm; ++tm; }
+      tn = tm + t;
+    } else { tm = tile / p.tiles_n; tn = tile % p.tiles_n; }
+    it.m0 = tm * TBM; it.n0 = tn * TBN; it.diag = (tm == tn);
+    const int kb_total = ((p.K + TBK - 1) / TBK) * p.kbatch;
+    const int per = (kb_total + p.splits - 1) / p.splits;
+    it.kb0 = sp * per; it.kb1 = min(kb_total, it.kb0 + per);
+    return it.kb1 > it.kb0;
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  auto tile_ptr = [&](int s, int which) { return smem + (size_t)s * STAGE_BYTES + (size_t)which * TILE_BYTES; };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const WorkItem it = decode_work(p, w);
-        for (int kb = it.kb0; kb < it.kb1; ++kb) {
-          const int b = kb / kblocks, kc = (kb % kblocks) * TBK;
-          tc::mbar_wait(&empty[s], ph ^ 1);
-          tc::mbar_arrive_expect_tx(&full[s], 2 * TILE_BYTES);
-          tc::tma_load_3d(tile_ptr(s, 0), &tmA, &full[s], kc, it.m0, b);
-          tc::tma_load_3d(tile_ptr(s, 1), &tmB, &full[s], kc, it.n0, b);
-          if (++s == TSTAGES) { s = 0; ph ^= 1; }
-        }
+  __device__ static int num_kb(const Params&, const Item& it) { return it.kb1 - it.kb0; }
+  __device__ static void load(const Params& p, const Item& it, int kbi, uint8_t* a, uint8_t* b, uint64_t* bar) {
+    const int kblocks = (p.K + TBK - 1) / TBK;
+    const int kb = it.kb0 + kbi;
+    const int bt = kb / kblocks, kc = (kb % kblocks) * TBK;
+    tc::tma_load_3d(a, &p.tmA, bar, kc, it.m0, bt);
+    tc::tma_load_3d(b, &p.tmB, bar, kc, it.n0, bt);
+  }
+  __device__ static void store(const Params& p, const Item& it, int row, int col0, float (&v)[32]) {
+    const int m = it.m0 + row, nb = it.n0 + col0;
+    if (m >= p.M || nb >= p.N) return;
+    const bool mirror = p.upper_only && !it.diag;
+    float* drow = p.D + (int64_t)m * p.ldd + nb;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = p.alpha * v[j];
+      if (nb + j < p.N) {
+        if (p.epi == EPI_MUL) x *= p.E[(int64_t)m * p.lde + nb + j];
+        else if (p.epi == EPI_DIV_OUTER) x = x / (p.dg[m] * p.da[nb + j] + p.damping);
       }
+      v[j] = x;
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_tf32(TBM, TBN);
-      int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const WorkItem it = decode_work(p, w);
-        tc::mbar_wait(&tempty[acc], aph ^ 1);
-        tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TBN;
-        uint32_t accum = 0;
-        for (int kb = it.kb0; kb < it.kb1; ++kb) {
-          tc::mbar_wait(&conv[s], ph);
-          tc::tc_fence_after();
-          const uint64_t ahi = tc::make_kmajor_sw128_desc(tc::smem_u32(tile_ptr(s, 0)));
-          const uint64_t bhi = tc::make_kmajor_sw128_desc(tc::smem_u32(tile_ptr(s, 1)));
-          const uint64_t alo = tc::make_kmajor_sw128_desc(tc::smem_u32(tile_ptr(s, 2)));
-          const uint64_t blo = tc::make_kmajor_sw128_desc(tc::smem_u32(tile_ptr(s, 3)));
+    if (!p.atomic && !mirror && (p.ldd & 3) == 0 && nb + 32 <= p.N) {
 #pragma unroll
-          for (int kk = 0; kk < TBK / 8; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);   // 8 fp32 = 32 B = 2 x 16 B
-            tc::mma_tf32(d_tmem, alo + adv, bhi + adv, idesc, accum);
-            tc::mma_tf32(d_tmem, ahi + adv, blo + adv, idesc, 1u);
-            tc::mma_tf32(d_tmem, ahi + adv, bhi + adv, idesc, 1u);
-            accum = 1u;
-          }
-          tc::tc_commit(&empty[s]);
-          if (++s == TSTAGES) { s = 0; ph ^= 1; }
-        }
-        tc::tc_commit(&tfull[acc]);
-        acc ^= 1; if (acc == 0) aph ^= 1;
-      }
-    }
-  } else if (warp < 6) {
-    const int t = threadIdx.x - 64;   // 0..127
-    int s = 0; uint32_t ph = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const WorkItem it = decode_work(p, w);
-      for (int kb = it.kb0; kb < it.kb1; ++kb) {
-        tc::mbar_wait(&full[s], ph);
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
 #pragma unroll
-        for (int which = 0; which < 2; ++which) {
-          const float4* src = reinterpret_cast<const float4*>(tile_ptr(s, which));
-          float4* dst = reinterpret_cast<float4*>(tile_ptr(s, which + 2));
-#pragma unroll
-          for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
-            const float4 v = src[t + i * 128];
-            float4 lo;
-            lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-            lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-            lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-            lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-            dst[t + i * 128] = lo;
-          }
-        }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&conv[s]);
-        if (++s == TSTAGES) { s = 0; ph ^= 1; }
-      }
-    }
-  } else {
-    const int q = warp & 3;   // TMEM lane quarter this warp may access
-    int acc = 0; uint32_t aph = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const WorkItem it = decode_work(p, w);
-      tc::mbar_wait(&tfull[acc], aph);
-      tc::tc_fence_after();
-      const int m = it.m0 + q * 32 + lane;
-      const bool mirror = p.upper_only && !it.diag;
-#pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
-        float v[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TBN + c * 32), v);
-        tc::tmem_ld_wait();
-        const int nb = it.n0 + c * 32;
-        if (m < p.M && nb < p.N) {
-          float* drow = p.D + (int64_t)m * p.ldd + nb;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = p.alpha * v[j];
-            if (nb + j < p.N) {
-              if (p.epi == EPI_MUL) x *= p.E[(int64_t)m * p.lde + nb + j];
-              else if (p.epi == EPI_DIV_OUTER) x = x / (p.dg[m] * p.da[nb + j] + p.damping);
-            }
-            v[j] = x;
-          }
-          if (!p.atomic && !mirror && (p.ldd & 3) == 0 && nb + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (nb + j >= p.N) continue;
-              if (p.atomic) {
-                atomicAdd(drow + j, v[j]);
-                if (mirror) atomicAdd(p.D + (int64_t)(nb + j) * p.ldd + m, v[j]);
-              } else {
-                drow[j] = v[j];
-                if (mirror) p.D[(int64_t)(nb + j) * p.ldd + m] = v[j];
-              }
-            }
-          }
+      for (int j = 0; j < 32; ++j) {
+        if (nb + j >= p.N) continue;
+        if (p.atomic) {
+          atomicAdd(drow + j, v[j]);
+          if (mirror) atomicAdd(p.D + (int64_t)(nb + j) * p.ldd + m, v[j]);
+        } else {
+          drow[j] = v[j];
+          if (mirror) p.D[(int64_t)(nb + j) * p.ldd + m] = v[j];
         }
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
-      acc ^= 1; if (acc == 0) aph ^= 1;
     }
   }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
-}
+};
 
 // ------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -227,6 +106,22 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// generic 3-D fp32 map, SWIZZLE_128B: dims {d0, d1, d2}, byte strides of d1/d2, box {32, box_rows, 1}
+int make_tmap_3d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                 uint64_t stride2_bytes, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return KFAC_ERR_CUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return KFAC_ERR_CUDA; }
+  return KFAC_OK;
+}
+
 // 3-D map {K, rows, kbatch} over a row-major fp32 matrix (ld elements) with box {32, 128, 1}
 static int make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t K, int64_t ld, int kbatch,
                      int64_t kb_stride) {
@@ -241,6 +136,16 @@ static int make_tmap(CUtensorMap* tm, const float* base, int64_t rows, int64_t K
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return KFAC_ERR_CUDA; }
   return KFAC_OK;
+}
+
+int tc_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
 }
 
 bool tc_gemm_supported(const TcGemmArgs& a) {
@@ -260,15 +165,15 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream) {
     int dev = 0;
     KFAC_CUDA(cudaGetDevice(&dev));
     KFAC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    KFAC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GemmPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)tc::PSMEM));
     attr = true;
   }
   const int kbatch = a.kbatch > 0 ? a.kbatch : 1;
-  CUtensorMap tmA, tmB;
-  int rc;
-  if ((rc = make_tmap(&tmA, a.A, a.M, a.K, a.lda, kbatch, a.a_kb_stride))) return rc;
-  if ((rc = make_tmap(&tmB, a.B, a.N, a.K, a.ldb, kbatch, a.b_kb_stride))) return rc;
   TcParams p{};
+  int rc;
+  if ((rc = make_tmap(&p.tmA, a.A, a.M, a.K, a.lda, kbatch, a.a_kb_stride))) return rc;
+  if ((rc = make_tmap(&p.tmB, a.B, a.N, a.K, a.ldb, kbatch, a.b_kb_stride))) return rc;
   p.D = a.D; p.ldd = a.ldd; p.M = a.M; p.N = a.N; p.K = a.K; p.kbatch = kbatch;
   p.tiles_m = ceil_div(a.M, TBM); p.tiles_n = ceil_div(a.N, TBN);
   p.upper_only = a.upper_only; p.atomic = a.atomic; p.alpha = a.alpha;
@@ -288,7 +193,7 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream) {
   p.splits = splits;
   const int total = ntiles * splits;
   const int grid = std::min(total, num_sms);
-  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tmA, tmB, p, total);
+  tc::pipeline_kernel<GemmPolicy><<<grid, tc::PTHREADS, tc::PSMEM, stream>>>(p, total);
   KFAC_LAUNCH_CHECK();
   return KFAC_OK;
 }

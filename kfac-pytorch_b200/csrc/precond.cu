@@ -107,7 +107,17 @@ int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, 
   t.A = A; t.lda = lda; t.B = B; t.ldb = ldb; t.D = D; t.ldd = ldd; t.M = M; t.N = N; t.K = K;
   t.kbatch = 1; t.alpha = 1.f; t.splits = 1;
   t.epi = e.kind; t.E = e.E; t.lde = e.lde; t.dg = e.dg; t.da = e.da; t.damping = e.damping;
-  if (M >= 64 && N >= 64 && K >= 32 && tc_gemm_supported(t)) return launch_tc_gemm(t, s);
+  if (M >= 64 && N >= 64 && K >= 32 && tc_gemm_supported(t)) {
+    if (e.kind == EPI_NONE && K > 1024) {
+      // long reductions: split K across CTAs and add the partial tiles with (round-to-
+      // nearest) L2 atomics -- the tensor-core accumulator truncates, so short chains
+      // keep the 3xTF32 result at fp32 accuracy, and small tile counts fill the SMs.
+      KFAC_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, s));
+      t.atomic = 1;
+      t.splits = ceil_div(K, 512);
+    }
+    return launch_tc_gemm(t, s);
+  }
   GemmArgs g{};
   g.A = A; g.sa_m = lda; g.sa_k = 1; g.B = B; g.sb_k = 1; g.sb_n = ldb;
   g.C = D; g.ldc = ldd; g.M = M; g.N = N; g.K = K; g.batch = 1; g.splitk = 1;

@@ -222,6 +222,13 @@ def test_eigh_batched_sizes(lib, dev, kind):
     print(kind, 'worst functional error', worst)
 
 
+def test_eigh_tc_class(lib, dev):
+    # n >= 384 takes the tcgen05 Gram/apply kernels (two pairs per 128-row MMA tile)
+    mats = [make_psd(384, 'cov', 1), make_psd(500, 'lowrank', 2), make_psd(576, 'cluster', 3), make_psd(640, 'ident', 4)]
+    for F, Q, d, _ in run_eigh(lib, dev, mats):
+        check_eigh(F, Q, d)
+
+
 def test_eigh_large(lib, dev):
     mats = [make_psd(1152, 'cov', 5), make_psd(1024, 'geo', 6)]
     for F, Q, d, _ in run_eigh(lib, dev, mats):
