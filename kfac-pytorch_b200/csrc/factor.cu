@@ -107,6 +107,16 @@ template <bool FEATURE_MAJOR>
 static int launch_cov(CovArgs a, int dtype, cudaStream_t s) {
   const int d = a.feat + a.ones;
   if (d <= 0 || a.rows <= 0 || a.batch <= 0) return KFAC_OK;
+  if (FEATURE_MAJOR && dtype == KFAC_F32 && a.ones == 0 && d >= 64 && (int64_t)a.rows * a.batch >= 256) {
+    // tcgen05 SYRK: X (features x samples) is a K-major operand as it lies in HBM;
+    // upper-triangular tiles only, split over the samples, partial tiles added with atomics.
+    TcGemmArgs t{};
+    t.A = (const float*)a.x; t.lda = a.ld; t.B = t.A; t.ldb = a.ld;
+    t.D = a.acc; t.ldd = d; t.M = d; t.N = d; t.K = a.rows;
+    t.kbatch = a.batch; t.a_kb_stride = a.batch_stride; t.b_kb_stride = a.batch_stride;
+    t.upper_only = 1; t.atomic = 1; t.splits = 0; t.alpha = a.scale;
+    if (tc_gemm_supported(t)) return launch_tc_gemm(t, s);
+  }
   const int nt = ceil_div(d, CT);
   const int tiles = nt * (nt + 1) / 2;
   int splits = ceil_div(148 * 3, (int64_t)tiles * a.batch);
@@ -126,16 +136,21 @@ static int launch_cov(CovArgs a, int dtype, cudaStream_t s) {
 struct Im2colArgs {
   const void* x; float* out;
   int batch, C, H, W, kh, kw, sh, sw, ph, pw, Ho, Wo;
+  int ones;        // append a feature row of ones
+  int64_t ld;      // leading dimension of the feature-major output (>= rows, multiple of 4)
 };
 template <typename T>
 __global__ void im2col_kernel(Im2colArgs a) {
   const int64_t rows = (int64_t)a.batch * a.Ho * a.Wo;
-  const int64_t total = rows * a.C * a.kh * a.kw;
+  const int nfeat = a.C * a.kh * a.kw;
+  const int64_t total = a.ld * (nfeat + a.ones);
   const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = idx % rows;
-    const int f = (int)(idx / rows);
+    const int64_t row = idx % a.ld;
+    const int f = (int)(idx / a.ld);
+    if (row >= rows) { a.out[idx] = 0.f; continue; }
+    if (f >= nfeat) { a.out[idx] = 1.f; continue; }
     const int wo = (int)(row % a.Wo);
     const int ho = (int)((row / a.Wo) % a.Ho);
     const int n = (int)(row / ((int64_t)a.Wo * a.Ho));
@@ -228,10 +243,10 @@ extern "C" int kfac_factor_linear(const void* x, int dtype, int64_t rows, int fe
 extern "C" size_t kfac_factor_conv2d_input_workspace_bytes(int batch, int C, int H, int W, int kh,
                                                            int kw, int sh, int sw, int ph, int pw,
                                                            int append_ones) {
-  (void)append_ones;
   if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0) return 0;
   const int64_t Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
-  return (size_t)batch * Ho * Wo * C * kh * kw * sizeof(float);
+  const int64_t ld = ((int64_t)batch * Ho * Wo + 3) / 4 * 4;
+  return (size_t)ld * ((size_t)C * kh * kw + (append_ones ? 1 : 0)) * sizeof(float);
 }
 
 extern "C" int kfac_factor_conv2d_input(const void* x, int dtype, int batch, int C, int H, int W,
@@ -259,15 +274,18 @@ extern "C" int kfac_factor_conv2d_input(const void* x, int dtype, int batch, int
   }
   const int64_t rows = (int64_t)batch * Ho * Wo;
   KFAC_CHECK_ARG(rows < (1ll << 31), "rows overflow");
-  Im2colArgs ia{x, (float*)ws, batch, C, H, W, kh, kw, sh, sw, ph, pw, Ho, Wo};
-  const int64_t total = rows * C * kh * kw;
+  const int64_t ld = (rows + 3) / 4 * 4;
+  Im2colArgs ia{x, (float*)ws, batch, C, H, W, kh, kw, sh, sw, ph, pw, Ho, Wo, a.ones, ld};
+  const int64_t total = ld * ((int64_t)C * kh * kw + a.ones);
   const int grid = grid_for(total) * 4;
   if (dtype == KFAC_F32) im2col_kernel<float><<<grid, 256, 0, s>>>(ia);
   else if (dtype == KFAC_F16) im2col_kernel<__half><<<grid, 256, 0, s>>>(ia);
   else if (dtype == KFAC_BF16) im2col_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(ia);
   else { set_error("unknown dtype %d", dtype); return KFAC_ERR_BAD_ARG; }
   KFAC_LAUNCH_CHECK();
-  a.x = ws; a.ld = rows; a.batch_stride = 0; a.rows = (int)rows; a.batch = 1; a.feat = C * kh * kw;
+  // the ones row is materialised, so the SYRK sees d = C*kh*kw + ones plain features
+  a.x = ws; a.ld = ld; a.batch_stride = 0; a.rows = (int)rows; a.batch = 1; a.feat = C * kh * kw + a.ones;
+  a.ones = 0;
   return launch_cov<true>(a, KFAC_F32, s);
 }
 

@@ -201,7 +201,7 @@ def check_eigh(F, Q, d, damping=1e-3, tol=1e-3):
     assert orth < 2e-4, ('orthogonality', n, orth)
     w, V = torch.linalg.eigh(F64)
     scale = max(float(w.abs().max()), 1e-30)
-    assert (torch.sort(d64).values - w.clamp(min=0)).abs().max().item() / scale < 2e-5
+    assert (torch.sort(d64).values - w.clamp(min=0)).abs().max().item() / scale < 5e-5
     f_ref = (V / (w.clamp(min=0) + damping * scale)) @ V.t()
     f_got = (Q64 / (d64 + damping * scale)) @ Q64.t()
     e = rel_fro(f_got, f_ref)

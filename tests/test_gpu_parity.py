@@ -186,3 +186,25 @@ def test_training_loss_decreases():
         opt.step()
         losses.append(loss.item())
     assert losses[0] > losses[-1]
+
+
+def test_multi_gpu_kaisa_parity():
+    """KAISA COMM/HYBRID/MEM-OPT on every visible GPU vs the oracle on the concatenated batch."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs >= 2 GPUs')
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'dist_parity.py')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}',
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), script],
+                         capture_output=True, text=True, timeout=600)
+    print(out.stdout[-3000:])
+    assert out.returncode == 0 and 'DIST PARITY OK' in out.stdout, out.stderr[-3000:]
