@@ -105,6 +105,8 @@ typedef struct kfac_eigh_item {
   float* d;
   int n;
   int ldq;        /* 0 -> n.  Multiples of 4 let the tensor-core GEMMs consume Q directly */
+  const float* V0T; /* optional warm start (n > 128): TRANSPOSE of an orthonormal starting basis,
+                       ld = ldq -- typically the QT of the previous call (may alias QT); NULL = identity */
 } kfac_eigh_item;
 size_t kfac_eigh_workspace_bytes(const int* n, int count);
 /* max_sweeps <= 0 -> default (30); tol <= 0 -> automatic (scaled with sqrt(n)) */

@@ -29,7 +29,7 @@ class EmaItem(C.Structure):
 
 
 class EighItem(C.Structure):
-    _fields_ = [('F', c_void_p), ('Q', c_void_p), ('QT', c_void_p), ('d', c_void_p), ('n', c_int), ('ldq', c_int)]
+    _fields_ = [('F', c_void_p), ('Q', c_void_p), ('QT', c_void_p), ('d', c_void_p), ('n', c_int), ('ldq', c_int), ('V0T', c_void_p)]
 
 
 class PrecondItem(C.Structure):

@@ -25,11 +25,12 @@ constexpr int JB = 32;        // block width
 constexpr int JP = 2 * JB;    // pair width
 constexpr int GR = 256;       // rows of G handled per CTA in gram/apply
 
-constexpr int TC_MIN_N = 384; // block matrices at least this large use the tcgen05 Gram/apply kernels
+constexpr int TC_MIN_N = 768; // block matrices at least this large use the tcgen05 Gram/apply kernels
 
 struct alignas(64) EighMat {
   CUtensorMap tmG, tmGt, tmV, tmW;   // mode 3 only (TMA views of G, G^T, V and the W^T pair buffers)
   const float* F; float* Q; float* QT; float* d;
+  const float* V0T;            // optional warm start: transposed previous eigenbasis (ld = ldq)
   int ldq;
   float* G; float* V;          // np x np
   float* Gt;                   // mode 3: transposed copy of G (K-major operand of the Gram)
@@ -67,10 +68,16 @@ __global__ void eigh_init_kernel(EighMat* mats, const int* block_list) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx / np), j = (int)(idx % np);
-    const float f = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
-    mt.G[idx] = f;
-    if (mt.mode == 3) mt.Gt[idx] = (i < n && j < n) ? mt.F[(int64_t)j * n + i] : 0.f;
-    mt.V[idx] = (i == j) ? 1.f : 0.f;
+    const bool in = (i < n && j < n);
+    if (mt.V0T) {
+      // warm start: V = V0; G = F V0 (and G^T) are produced by GEMMs right after this kernel
+      mt.V[idx] = in ? mt.V0T[(int64_t)j * mt.ldq + i] : (i == j ? 1.f : 0.f);
+      if (!in) { mt.G[idx] = 0.f; if (mt.mode == 3) mt.Gt[idx] = 0.f; }
+    } else {
+      mt.G[idx] = in ? mt.F[(int64_t)i * n + j] : 0.f;
+      if (mt.mode == 3) mt.Gt[idx] = in ? mt.F[(int64_t)j * n + i] : 0.f;
+      mt.V[idx] = (i == j) ? 1.f : 0.f;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; }
 }
@@ -459,6 +466,8 @@ struct ApplyPolicy {
   }
 };
 
+int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
+                  int K, cudaStream_t s);
 int make_tmap_3d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                  uint64_t stride2_bytes, uint32_t box_rows);
 
@@ -570,6 +579,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
   for (int i = 0; i < count; ++i) {
     EighMat& m = pl.mats[i];
     m.F = items[i].F; m.Q = items[i].Q; m.QT = items[i].QT; m.d = items[i].d;
+    m.V0T = (m.mode >= 2) ? items[i].V0T : nullptr;
     m.ldq = items[i].ldq > 0 ? items[i].ldq : items[i].n;
     m.tol = tol > 0.f ? tol : 1e-6f * sqrtf(fmaxf(1.f, (float)m.n / 16.f));
     if (m.mode >= 2) {
@@ -635,6 +645,14 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
   if (nblock > 0) {
     eigh_init_kernel<<<dim3(256, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();
+    for (int i = 0; i < count; ++i) {
+      const EighMat& m = pl.mats[i];
+      if (m.mode < 2 || !m.V0T) continue;
+      // G[i][j] = sum_k F[i][k] V0[k][j]  (TN: A = F, B = V0^T);  G^T[i][j] = sum_k V0^T[i][k] F[j][k]
+      int rc;
+      if ((rc = gemm_tn_plain(m.F, m.n, m.V0T, m.ldq, m.G, m.np, m.n, m.n, m.n, s))) return rc;
+      if (m.mode == 3 && (rc = gemm_tn_plain(m.V0T, m.ldq, m.F, m.n, m.Gt, m.np, m.n, m.n, m.n, s))) return rc;
+    }
     const int rps = pl.max_nb - 1;                 // rounds per sweep of the largest matrix
     const int chunks = ceil_div(std::max(1, pl.simt_max_rows), GR);
     // tcgen05 class launch geometry

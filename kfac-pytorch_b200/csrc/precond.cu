@@ -126,6 +126,11 @@ int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, 
   return launch_gemm(g, s);
 }
 
+int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
+                  int K, cudaStream_t s) {
+  return gemm_tn(A, lda, B, ldb, D, ldd, M, N, K, Epi{}, s);
+}
+
 }  // namespace kfac
 
 using namespace kfac;

@@ -352,3 +352,27 @@ def test_triu_pack_unpack(lib, dev, n):
     assert lib.kfac_scale_inplace(out.data_ptr(), n * n, 0.5, S()) == 0
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), 0.5 * F)
+
+
+def test_eigh_warm_start(lib, dev):
+    """Second decomposition seeded with the previous eigenbasis (V0T = QT of the first call)."""
+    from kfac_b200 import _cabi
+    torch.manual_seed(0)
+    for n in (200, 576, 1024):
+        F1 = make_psd(n, 'cov', n)
+        F2 = (0.95 * F1 + 0.05 * make_psd(n, 'cov', n + 7)).contiguous()
+        ld = _cabi.ld4(n)
+        Q = torch.zeros(n, ld, device=dev)
+        QT = torch.zeros(n, ld, device=dev)
+        d = torch.empty(n, device=dev)
+        ns = (C.c_int * 1)(n)
+        need = lib.kfac_eigh_workspace_bytes(ns, 1)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        for F, warm in ((F1, None), (F2, QT)):
+            Fd = F.to(dev)
+            items = (_cabi.EighItem * 1)(_cabi.EighItem(Fd.data_ptr(), Q.data_ptr(), QT.data_ptr(), d.data_ptr(), n, ld,
+                                                       warm.data_ptr() if warm is not None else None))
+            assert lib.kfac_eigh_batched(items, 1, ws.data_ptr(), need, 0, 0.0, S()) == 0, lib.kfac_last_error()
+            torch.cuda.synchronize()
+            check_eigh(Fd, Q[:, :n], d)
+            assert torch.equal(QT[:, :n], Q[:, :n].t())
