@@ -40,6 +40,7 @@ struct alignas(64) EighMat {
   int gram_base;               // mode 3: first Gram item (two pairs per 128-row MMA tile)
   float tol;
   unsigned int sweep_off;      // float bits, atomicMax
+  float prev_off;              // convergence measure of the previous sweep
   int done;
   int sweeps;
 };
@@ -53,8 +54,14 @@ __device__ __forceinline__ void tournament(int r, int k, int nb, int& p, int& q)
   p = min(a, b); q = max(a, b);
 }
 
+// Convergence measure of a column pair in Gram space (M = G^T G, M_ii = lambda_i^2):
+// |g_p . g_q| / max(|g_p|^2, |g_q|^2) ~ the amplitude with which the two eigenvectors
+// still contaminate each other.  (The classical |.|/sqrt(M_pp M_qq) asks for RELATIVE
+// accuracy of tiny eigenvalues, which fp32 Grams of graded factors cannot deliver --
+// the sweeps would chase rounding noise forever -- and which K-FAC does not need:
+// everything below the damping is flattened by 1/(dg*da + damping).)
 __device__ __forceinline__ float rel_off(float apq, float app, float aqq) {
-  const float den = sqrtf(fabsf(app * aqq));
+  const float den = fmaxf(fabsf(app), fabsf(aqq));
   const float x = fabsf(apq);
   if (x == 0.f) return 0.f;
   return den > 0.f ? x / den : 1e30f;
@@ -79,7 +86,7 @@ __global__ void eigh_init_kernel(EighMat* mats, const int* block_list) {
       mt.V[idx] = (i == j) ? 1.f : 0.f;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; mt.prev_off = 1e30f; }
 }
 
 __global__ void eigh_final_kernel(EighMat* mats, const int* block_list) {
@@ -242,7 +249,8 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
         tournament(st, tid, N, p, q);
         const float apq = M[p][q], app = M[p][p], aqq = M[q][q];
         float c = 1.f, s = 0.f;
-        if (fabsf(apq) > tol_in * sqrtf(fabsf(app * aqq))) {
+        const float thr = mode_block ? fmaxf(fabsf(app), fabsf(aqq)) : sqrtf(fabsf(app * aqq));
+        if (fabsf(apq) > tol_in * thr) {
           const float tau = (aqq - app) / (2.f * apq);
           const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
           c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's bias makes column norms drift
@@ -373,7 +381,11 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
     if (mt.done) continue;
     if ((round + 1) % (mt.nb - 1) == 0) {
       mt.sweeps += 1;
-      if (__uint_as_float(mt.sweep_off) < mt.tol) mt.done = 1;
+      const float off = __uint_as_float(mt.sweep_off);
+      if (off < mt.tol) mt.done = 1;
+      // safety net: stalled at the rounding floor (no longer shrinking, already small)
+      else if (mt.sweeps >= 4 && off < 1e-3f && off > 0.7f * mt.prev_off) mt.done = 1;
+      mt.prev_off = off;
       mt.sweep_off = 0u;
     }
     if (!mt.done) pending = 1;
@@ -581,7 +593,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     m.F = items[i].F; m.Q = items[i].Q; m.QT = items[i].QT; m.d = items[i].d;
     m.V0T = (m.mode >= 2) ? items[i].V0T : nullptr;
     m.ldq = items[i].ldq > 0 ? items[i].ldq : items[i].n;
-    m.tol = tol > 0.f ? tol : 1e-6f * sqrtf(fmaxf(1.f, (float)m.n / 16.f));
+    m.tol = tol > 0.f ? tol : 2e-6f;   // residual eigenvector contamination (see rel_off)
     if (m.mode >= 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
       if (m.mode == 3) {
