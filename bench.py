@@ -150,6 +150,30 @@ def algorithmic_work(pre):
     return eig, prec
 
 
+def tc_gemm_microbench(lib, dev, n=4096, iters=10):
+    """Isolated timing of the tcgen05 GEMM engine (the kernel under K3/K5/K8):
+    D = A B^T, n^3 problem, fp32 operands (3 x 64 MB > 126 MB L2), CUDA events."""
+    A = torch.randn(n, n, device=dev)
+    B = torch.randn(n, n, device=dev)
+    D = torch.empty(n, n, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        rc = lib.kfac_gemm_tn_tc(A.data_ptr(), n, B.data_ptr(), n, D.data_ptr(), n, n, n, n, 1.0, 0, 1, s)
+        assert rc == 0, lib.kfac_last_error()
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return 2.0 * n ** 3 / (ms / 1e3) / 1e12, ms
+
+
 # ------------------------------------------------------------------ own arm
 def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -253,6 +277,8 @@ def run_b200(args):
         if pre._assignment.inv_worker(name, 'G') == r:
             my_eig += 9.0 * l.g_dim ** 3
     achieved = (my_eig / (inv_ms / 1e3) / 1e12) if inv_ms > 0 else 0.0
+    gemm_tf, gemm_ms = tc_gemm_microbench(lib, dev) if rank == 0 else (0.0, 0.0)
+    burst_peak = float(peaks.get('bf16_tflops', 1590.0))
     out = {
         'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / K, 'higher_is_better': True,
@@ -265,12 +291,23 @@ def run_b200(args):
                 'h2d_bytes_per_step': host_x.numel() * 4 + host_y.numel() * 8, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'kfac_phase_ms_per_step': {k: v / K for k, v in sorted(phase_ms.items())},
-        'roofline': {'kernel': 'kfac_eigh_batched (block one-sided Jacobi: gram/jacobi_smem/apply rounds)',
-                     'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s',
-                     'frac': achieved / tensor_peak if tensor_peak else None, 'traffic': None,
-                     'convention': '9 n^3 flop per eigendecomposition (SURVEY.md 8d), rank-0 share, '
-                                   'duration = CUDA-event time of the inverse phase per step',
-                     'peak_source': peak_src},
+        # dominant KERNEL: the tcgen05 pipeline (Gram/apply of the eigensolver, precondition and
+        # SYRK GEMMs are instances of it), timed alone on a 4096^3 problem
+        'roofline': {'kernel': 'tc::pipeline_kernel<GemmPolicy> (tcgen05 3xTF32 GEMM engine), 4096^3, isolated',
+                     'bound': 'tensor', 'achieved': gemm_tf, 'peak': burst_peak, 'unit': 'TFLOP/s',
+                     'frac': gemm_tf / burst_peak if burst_peak else None, 'traffic': None,
+                     'ms_per_launch': gemm_ms,
+                     'convention': 'algorithmic fp32 flops 2*M*N*K per launch / CUDA-event time; every product is '
+                                   'issued as 3 TF32 MMAs, so the tensor pipe executes 3x these flops at the TF32 '
+                                   'rate (= half the bf16 rate the peak was measured with)',
+                     'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if peaks else 'fallback 1590'},
+        # dominant PHASE of the step: the batched eigensolver
+        'roofline_phase': {'phase': 'kfac_eigh_batched (block one-sided Jacobi: Gram / smem Jacobi / apply rounds)',
+                           'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s',
+                           'frac': achieved / tensor_peak if tensor_peak else None,
+                           'convention': '9 n^3 flop per eigendecomposition (SURVEY.md 8d), rank-0 share, '
+                                         'duration = CUDA-event time of the inverse phase per step',
+                           'peak_source': peak_src},
         'algorithmic_flops_per_step': {'eigh_9n3': eig_flops, 'precondition_4ga(g+a)': prec_flops},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
