@@ -38,6 +38,7 @@ struct alignas(64) EighMat {
   int* pair_skip;              // pairs
   int n, np, nb, pair_base, mode;
   int gram_base;               // mode 3: first Gram item (two pairs per 128-row MMA tile)
+  int inner_base;              // first pair of this matrix in the unified (SIMT + TC) pair list
   float tol;
   unsigned int sweep_off;      // float bits, atomicMax
   float prev_off;              // convergence measure of the previous sweep
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
   float* Mg = nullptr;
   if (mode_block) {
     if (mt.done) return;
-    local = blockIdx.x - mt.pair_base;
+    local = blockIdx.x - mt.inner_base;
     Mg = mt.M + (int64_t)local * JP * JP;
     for (int idx = tid; idx < N * N; idx += T) {
       const int i = idx / N, j = idx % N;
@@ -489,7 +490,7 @@ struct EighPlan {
   std::vector<int> pair_mat, block_list, d64_list, d128_list;
   std::vector<int> tc_pair_mat, tc_gram_mat, simt_list;
   size_t off_mats, off_pair_mat, off_block, off_d64, off_d128, off_flag, off_data, total;
-  size_t off_tc_pair, off_tc_gram, off_simt;
+  size_t off_tc_pair, off_tc_gram, off_simt, off_all_pair;
   int total_pairs, max_nb, max_rows;
   int tc_pairs, tc_gram_items, tc_max_rows, simt_max_rows;
 };
@@ -539,7 +540,14 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
   pl.off_block = take(sizeof(int) * std::max<size_t>(1, pl.block_list.size()));
   pl.off_d64 = take(sizeof(int) * std::max<size_t>(1, pl.d64_list.size()));
   pl.off_d128 = take(sizeof(int) * std::max<size_t>(1, pl.d128_list.size()));
+  // unified pair list for the shared-memory Jacobi: SIMT-class pairs, then tensor-core-class pairs
+  for (int i = 0; i < count; ++i) {
+    EighMat& m = pl.mats[i];
+    if (m.mode == 2) m.inner_base = m.pair_base;
+    else if (m.mode == 3) m.inner_base = pl.total_pairs + m.pair_base;
+  }
   pl.off_flag = take(sizeof(int) * 4);
+  pl.off_all_pair = take(sizeof(int) * std::max<size_t>(1, pl.pair_mat.size() + pl.tc_pair_mat.size()));
   pl.off_tc_pair = take(sizeof(int) * std::max<size_t>(1, pl.tc_pair_mat.size()));
   pl.off_tc_gram = take(sizeof(int) * std::max<size_t>(1, pl.tc_gram_mat.size()));
   pl.off_simt = take(sizeof(int) * std::max<size_t>(1, pl.simt_list.size()));
@@ -628,6 +636,12 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     KFAC_CUDA(cudaMemcpyAsync(d_d64, pl.d64_list.data(), sizeof(int) * pl.d64_list.size(), cudaMemcpyHostToDevice, s));
   if (!pl.d128_list.empty())
     KFAC_CUDA(cudaMemcpyAsync(d_d128, pl.d128_list.data(), sizeof(int) * pl.d128_list.size(), cudaMemcpyHostToDevice, s));
+  int* d_all_pair = (int*)(base + pl.off_all_pair);
+  if (!pl.pair_mat.empty())
+    KFAC_CUDA(cudaMemcpyAsync(d_all_pair, pl.pair_mat.data(), sizeof(int) * pl.pair_mat.size(), cudaMemcpyHostToDevice, s));
+  if (!pl.tc_pair_mat.empty())
+    KFAC_CUDA(cudaMemcpyAsync(d_all_pair + pl.pair_mat.size(), pl.tc_pair_mat.data(), sizeof(int) * pl.tc_pair_mat.size(),
+                              cudaMemcpyHostToDevice, s));
   int* d_tc_pair = (int*)(base + pl.off_tc_pair);
   int* d_tc_gram = (int*)(base + pl.off_tc_gram);
   if (!pl.tc_pair_mat.empty()) {
@@ -697,18 +711,25 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     for (int sw = 0; sw < max_sweeps; ++sw) {
       for (int rr = 0; rr < rps; ++rr) {
         const int r = sw * rps + rr;
+        // Gram of both classes, ONE shared-memory Jacobi launch over all pairs, then the applies
         if (pl.total_pairs > 0) {
           eigh_gram_kernel<<<dim3(pl.total_pairs, chunks), 256, 0, s>>>(d_mats, d_pair_mat, r);
-          jacobi_smem_kernel<64><<<pl.total_pairs, 256, smem64, s>>>(d_mats, d_pair_mat, 1, inner_sweeps);
-          eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
-          count_launch(3);
+          count_launch(1);
         }
         if (pl.tc_pairs > 0) {
           gp.round = r; ap.round = r;
           tc::pipeline_kernel<GramPolicy><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
-          jacobi_smem_kernel<64><<<pl.tc_pairs, 256, smem64, s>>>(d_mats, d_tc_pair, 1, inner_sweeps);
+          count_launch(1);
+        }
+        jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 256, smem64, s>>>(d_mats, d_all_pair, 1, inner_sweeps);
+        count_launch(1);
+        if (pl.total_pairs > 0) {
+          eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
+          count_launch(1);
+        }
+        if (pl.tc_pairs > 0) {
           tc::pipeline_kernel<ApplyPolicy><<<std::min(apply_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(ap, apply_total);
-          count_launch(3);
+          count_launch(1);
         }
         eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r, d_flag);
       }
