@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "tc_pipeline.cuh"
 
+#include <stdlib.h>
+
 #include <vector>
 
 namespace kfac {
@@ -42,6 +44,8 @@ struct alignas(64) EighMat {
   float tol;
   unsigned int sweep_off;      // float bits, atomicMax
   float prev_off;              // convergence measure of the previous sweep
+  unsigned int max_diag;       // float bits: largest |g_j|^2 seen (lambda_max^2), atomicMax
+  float nw_ratio;              // normwise relaxation, see pair_den()
   int done;
   int sweeps;
 };
@@ -61,8 +65,18 @@ __device__ __forceinline__ void tournament(int r, int k, int nb, int& p, int& q)
 // accuracy of tiny eigenvalues, which fp32 Grams of graded factors cannot deliver --
 // the sweeps would chase rounding noise forever -- and which K-FAC does not need:
 // everything below the damping is flattened by 1/(dg*da + damping).)
-__device__ __forceinline__ float rel_off(float apq, float app, float aqq) {
+//
+// Pairs of columns that are BOTH small next to the largest column carry absolute
+// rounding noise ~eps*lambda_max from their history of rotations, so their mutual
+// measure can never reach the tolerance; for them the test relaxes to the normwise
+// backward-stable form |g_p.g_q| <= tol_n * lambda_max * max(|g_p|,|g_q|) with
+// tol_n = nw_ratio*tol ~ 3e-6/sqrt(n) (what LAPACK-class fp32 solvers deliver).
+__device__ __forceinline__ float pair_den(float app, float aqq, float max_diag, float nw_ratio) {
   const float den = fmaxf(fabsf(app), fabsf(aqq));
+  return fmaxf(den, nw_ratio * sqrtf(max_diag * den));
+}
+__device__ __forceinline__ float rel_off(float apq, float app, float aqq, float max_diag, float nw_ratio) {
+  const float den = pair_den(app, aqq, max_diag, nw_ratio);
   const float x = fabsf(apq);
   if (x == 0.f) return 0.f;
   return den > 0.f ? x / den : 1e30f;
@@ -87,7 +101,7 @@ __global__ void eigh_init_kernel(EighMat* mats, const int* block_list) {
       mt.V[idx] = (i == j) ? 1.f : 0.f;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; mt.prev_off = 1e30f; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; mt.prev_off = 1e30f; mt.max_diag = 0u; }
 }
 
 __global__ void eigh_final_kernel(EighMat* mats, const int* block_list) {
@@ -215,10 +229,15 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
   const float tol = mt.tol;
   if (mode_block) {
     // largest relative off-diagonal of this pair's Gram (convergence measure)
+    float dmax = 0.f;
+    for (int j = tid; j < N; j += T) dmax = fmaxf(dmax, M[j][j]);
+    if (dmax > 0.f) atomicMax(&mt.max_diag, __float_as_uint(dmax));
+    const float max_diag = __uint_as_float(mt.max_diag);   // running maximum over all rounds
+    const float nw_ratio = mt.nw_ratio;
     float mx = 0.f;
     for (int idx = tid; idx < N * N; idx += T) {
       const int i = idx / N, j = idx % N;
-      if (j > i) mx = fmaxf(mx, rel_off(M[i][j], M[i][i], M[j][j]));
+      if (j > i) mx = fmaxf(mx, rel_off(M[i][j], M[i][i], M[j][j], max_diag, nw_ratio));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -239,6 +258,8 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
     if (mx < tol) return;
   }
   const float tol_in = mode_block ? fminf(tol * 0.125f, 1e-6f) : 1e-7f;
+  const float blk_max_diag = mode_block ? __uint_as_float(mt.max_diag) : 0.f;
+  const float blk_nw_ratio = mode_block ? mt.nw_ratio : 0.f;
 
   int* pq = reinterpret_cast<int*>(cs + N);   // (p,q) of every pair of the current step
   for (int sweep = 0; sweep < max_inner; ++sweep) {
@@ -250,7 +271,7 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
         tournament(st, tid, N, p, q);
         const float apq = M[p][q], app = M[p][p], aqq = M[q][q];
         float c = 1.f, s = 0.f;
-        const float thr = mode_block ? fmaxf(fabsf(app), fabsf(aqq)) : sqrtf(fabsf(app * aqq));
+        const float thr = mode_block ? pair_den(app, aqq, blk_max_diag, blk_nw_ratio) : sqrtf(fabsf(app * aqq));
         if (fabsf(apq) > tol_in * thr) {
           const float tau = (aqq - app) / (2.f * apq);
           const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
@@ -602,6 +623,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     m.V0T = (m.mode >= 2) ? items[i].V0T : nullptr;
     m.ldq = items[i].ldq > 0 ? items[i].ldq : items[i].n;
     m.tol = tol > 0.f ? tol : 2e-6f;   // residual eigenvector contamination (see rel_off)
+    m.nw_ratio = (3e-6f / sqrtf((float)m.n)) / m.tol;
     if (m.mode >= 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
       if (m.mode == 3) {
@@ -744,6 +766,15 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     }
     eigh_final_kernel<<<dim3(64, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();
+    if (getenv("KFAC_EIGH_DEBUG")) {   // diagnostics only: per-matrix sweep counts (synchronises)
+      std::vector<EighMat> back(count);
+      KFAC_CUDA(cudaStreamSynchronize(s));
+      KFAC_CUDA(cudaMemcpy(back.data(), d_mats, sizeof(EighMat) * count, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < count; ++i)
+        if (back[i].mode >= 2)
+          fprintf(stderr, "[kfac eigh] n=%d mode=%d warm=%d sweeps=%d done=%d last_off=%.2e\n", back[i].n,
+                  back[i].mode, back[i].V0T != nullptr, back[i].sweeps, back[i].done, back[i].prev_off);
+    }
   }
   return KFAC_OK;
 }

@@ -208,3 +208,49 @@ def test_multi_gpu_kaisa_parity():
                          capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:])
     assert out.returncode == 0 and 'DIST PARITY OK' in out.stdout, out.stderr[-3000:]
+
+
+def test_linear_stack_parity():
+    """BASELINE.json configs[4] shapes at reduced width: a GPT-NeoX-like stack of
+    biased Linear layers fed (batch*seq, hidden) token activations (TP=1: the
+    math of kfac/gpt_neox/layer.py:238-247 equals kfac/layers/eigen.py:374-385)."""
+    class Stack(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.qkv = torch.nn.Linear(96, 288)
+            self.proj = torch.nn.Linear(288, 96)
+            self.up = torch.nn.Linear(96, 384)
+            self.down = torch.nn.Linear(384, 96)
+
+        def forward(self, x):          # x: (batch, seq, hidden) -- leading dims are flattened by K-FAC
+            h = torch.tanh(self.proj(torch.tanh(self.qkv(x))))
+            return self.down(torch.nn.functional.gelu(self.up(h)))
+
+    torch.manual_seed(4)
+    x = torch.randn(4, 64, 96)
+    y = torch.randn(4, 64, 96)
+    worst = _parity_vs_oracle(Stack, x, y, torch.nn.MSELoss(), steps=3, damping=0.003)
+    print('linear stack worst P rel-fro', worst)
+
+
+def test_grad_scaler_unscales_g_factor():
+    """AMP-style loss scaling (kfac/layers/base.py:365-366): G statistics are divided by the scale."""
+    from kfac_b200.preconditioner import KFACPreconditioner
+    from oracle.models import TinyModel
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    base = TinyModel().to(dev)
+    x, y = torch.rand(4, 10, device=dev), torch.rand(4, 10, device=dev)
+    crit = torch.nn.MSELoss(reduction='sum')
+    outs = []
+    for scale in (1.0, 128.0):
+        m = copy.deepcopy(base)
+        p = KFACPreconditioner(m, grad_scaler=(lambda s=scale: s) if scale != 1.0 else None)
+        (crit(m(x), y) * scale).backward()
+        for q in m.parameters():
+            q.grad /= scale               # what GradScaler.unscale_ does before step()
+        p.step()
+        torch.cuda.synchronize()
+        outs.append([q.grad.clone() for q in m.parameters()])
+    for a, b in zip(*outs):
+        assert rel_fro(a, b) < 1e-4
