@@ -27,7 +27,15 @@ constexpr int JB = 32;        // block width
 constexpr int JP = 2 * JB;    // pair width
 constexpr int GR = 256;       // rows of G handled per CTA in gram/apply
 
-constexpr int TC_MIN_N = 768; // block matrices at least this large use the tcgen05 Gram/apply kernels
+constexpr int TC_MIN_N = 768;
+// 1: the Gram reads G itself as an MN-major operand (no transposed copy of G is kept);
+// 0: the Gram reads a K-major G^T that the apply kernel refreshes.
+// (runtime switch for A/B testing: env KFAC_GRAM_KMAJOR=1 selects the G^T variant)
+static bool gram_mn_major() {
+  static int v = -1;
+  if (v < 0) v = getenv("KFAC_GRAM_KMAJOR") ? 0 : 1;
+  return v != 0;
+} // block matrices at least this large use the tcgen05 Gram/apply kernels
 
 struct alignas(64) EighMat {
   CUtensorMap tmG, tmGt, tmV, tmW;   // mode 3 only (TMA views of G, G^T, V and the W^T pair buffers)
@@ -94,10 +102,10 @@ __global__ void eigh_init_kernel(EighMat* mats, const int* block_list) {
     if (mt.V0T) {
       // warm start: V = V0; G = F V0 (and G^T) are produced by GEMMs right after this kernel
       mt.V[idx] = in ? mt.V0T[(int64_t)j * mt.ldq + i] : (i == j ? 1.f : 0.f);
-      if (!in) { mt.G[idx] = 0.f; if (mt.mode == 3) mt.Gt[idx] = 0.f; }
+      if (!in) { mt.G[idx] = 0.f; if (mt.Gt) mt.Gt[idx] = 0.f; }
     } else {
       mt.G[idx] = in ? mt.F[(int64_t)i * n + j] : 0.f;
-      if (mt.mode == 3) mt.Gt[idx] = in ? mt.F[(int64_t)j * n + i] : 0.f;
+      if (mt.Gt) mt.Gt[idx] = in ? mt.F[(int64_t)j * n + i] : 0.f;
       mt.V[idx] = (i == j) ? 1.f : 0.f;
     }
   }
@@ -422,11 +430,13 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
 // G^T (K-major, K = row index of G), D[128x128] = A A^T; the two diagonal 64x64
 // quadrants are the pair Grams (the off-diagonal quadrants are discarded).
 struct GramParams { EighMat* mats; const int* item_mat; int ksplits; int round; };
-struct GramPolicy {
+template <bool MN>
+struct GramPolicyT {
   using Params = GramParams;
   struct Item { EighMat* mt; int p0, I1, J1, I2, J2, kb0, kb1; };
   static constexpr int BN = 128;
   static constexpr bool B_IS_A = true;
+  static constexpr bool MN_MAJOR = MN;
   static constexpr uint32_t TX_BYTES = tc::PTILE;
   __device__ static bool decode(const Params& p, int w, Item& it) {
     const int gi = w / p.ksplits, sp = w % p.ksplits;
@@ -445,10 +455,17 @@ struct GramPolicy {
   __device__ static int num_kb(const Params&, const Item& it) { return it.kb1 - it.kb0; }
   __device__ static void load(const Params&, const Item& it, int kbi, uint8_t* a, uint8_t*, uint64_t* bar) {
     const int kc = (it.kb0 + kbi) * 32;
-    tc::tma_load_3d(a, &it.mt->tmGt, bar, kc, it.I1 * JB, 0);
-    tc::tma_load_3d(a + 4096, &it.mt->tmGt, bar, kc, it.J1 * JB, 0);
-    tc::tma_load_3d(a + 8192, &it.mt->tmGt, bar, kc, it.I2 * JB, 0);
-    tc::tma_load_3d(a + 12288, &it.mt->tmGt, bar, kc, it.J2 * JB, 0);
+    if (MN_MAJOR) {   // boxes {32 columns of a block, 32 rows kc..kc+31} of G
+      tc::tma_load_3d(a, &it.mt->tmGt, bar, it.I1 * JB, kc, 0);
+      tc::tma_load_3d(a + 4096, &it.mt->tmGt, bar, it.J1 * JB, kc, 0);
+      tc::tma_load_3d(a + 8192, &it.mt->tmGt, bar, it.I2 * JB, kc, 0);
+      tc::tma_load_3d(a + 12288, &it.mt->tmGt, bar, it.J2 * JB, kc, 0);
+    } else {          // boxes {32 reduction indices, 32 rows of G^T}
+      tc::tma_load_3d(a, &it.mt->tmGt, bar, kc, it.I1 * JB, 0);
+      tc::tma_load_3d(a + 4096, &it.mt->tmGt, bar, kc, it.J1 * JB, 0);
+      tc::tma_load_3d(a + 8192, &it.mt->tmGt, bar, kc, it.I2 * JB, 0);
+      tc::tma_load_3d(a + 12288, &it.mt->tmGt, bar, kc, it.J2 * JB, 0);
+    }
   }
   __device__ static void store(const Params&, const Item& it, int row, int col0, float (&v)[32]) {
     float* M;
@@ -466,6 +483,7 @@ struct ApplyPolicy {
   struct Item { EighMat* mt; int local, I, J, m0, which; };
   static constexpr int BN = 64;
   static constexpr bool B_IS_A = false;
+  static constexpr bool MN_MAJOR = false;
   static constexpr uint32_t TX_BYTES = tc::PTILE + 64 * 32 * 4;
   __device__ static bool decode(const Params& p, int w, Item& it) {
     it.which = w & 1;
@@ -492,7 +510,7 @@ struct ApplyPolicy {
     float* X = (it.which ? it.mt->V : it.mt->G) + (int64_t)r * np + cb;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(X + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    if (!it.which) {
+    if (!it.which && it.mt->Gt) {
       float* T = it.mt->Gt + (int64_t)cb * np + r;   // lanes hold consecutive rows r: coalesced columns of G^T
 #pragma unroll
       for (int j = 0; j < 32; ++j) T[(int64_t)j * np] = v[j];
@@ -579,7 +597,7 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
     const size_t sq = (size_t)m.np * m.np * sizeof(float);
     const size_t pb = (size_t)(m.nb / 2) * JP * JP * sizeof(float);
     m.G = (float*)take(sq); m.V = (float*)take(sq);      // offsets, rebased later
-    if (m.mode == 3) m.Gt = (float*)take(sq);
+    if (m.mode == 3 && !gram_mn_major()) m.Gt = (float*)take(sq);
     m.M = (float*)take(pb); m.W = (float*)take(pb);
     m.pair_skip = (int*)take(sizeof(int) * (m.nb / 2));
   }
@@ -627,13 +645,13 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     if (m.mode >= 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
       if (m.mode == 3) {
-        m.Gt = (float*)(base + (size_t)m.Gt);
+        m.Gt = gram_mn_major() ? nullptr : (float*)(base + (size_t)m.Gt);
         const uint64_t np = m.np, rowb = np * 4;
         int rc;
         // G / V: 128-row x 32-column boxes; G^T: 32-row boxes; W^T pair buffers as {k, j, pair}
         if ((rc = make_tmap_3d(&m.tmG, m.G, np, np, 1, rowb, rowb * np, 128))) return rc;
         if ((rc = make_tmap_3d(&m.tmV, m.V, np, np, 1, rowb, rowb * np, 128))) return rc;
-        if ((rc = make_tmap_3d(&m.tmGt, m.Gt, np, np, 1, rowb, rowb * np, 32))) return rc;
+        if ((rc = make_tmap_3d(&m.tmGt, gram_mn_major() ? m.G : m.Gt, np, np, 1, rowb, rowb * np, 32))) return rc;
       }
       m.M = (float*)(base + (size_t)m.M); m.W = (float*)(base + (size_t)m.W);
       m.pair_skip = (int*)(base + (size_t)m.pair_skip);
@@ -699,7 +717,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
       // G[i][j] = sum_k F[i][k] V0[k][j]  (TN: A = F, B = V0^T);  G^T[i][j] = sum_k V0^T[i][k] F[j][k]
       int rc;
       if ((rc = gemm_tn_plain(m.F, m.n, m.V0T, m.ldq, m.G, m.np, m.n, m.n, m.n, s))) return rc;
-      if (m.mode == 3 && (rc = gemm_tn_plain(m.V0T, m.ldq, m.F, m.n, m.Gt, m.np, m.n, m.n, m.n, s))) return rc;
+      if (m.Gt && (rc = gemm_tn_plain(m.V0T, m.ldq, m.F, m.n, m.Gt, m.np, m.n, m.n, m.n, s))) return rc;
     }
     const int rps = pl.max_nb - 1;                 // rounds per sweep of the largest matrix
     const int chunks = ceil_div(std::max(1, pl.simt_max_rows), GR);
@@ -707,7 +725,8 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     const int sms = tc_num_sms();
     static bool tc_attr = false;
     if (!tc_attr && pl.tc_pairs > 0) {
-      KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
+      KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicyT<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
+      KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicyT<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
       KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<ApplyPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
       tc_attr = true;
     }
@@ -740,7 +759,10 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
         }
         if (pl.tc_pairs > 0) {
           gp.round = r; ap.round = r;
-          tc::pipeline_kernel<GramPolicy><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
+          if (gram_mn_major())
+            tc::pipeline_kernel<GramPolicyT<true>><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
+          else
+            tc::pipeline_kernel<GramPolicyT<false>><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
           count_launch(1);
         }
         jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 256, smem64, s>>>(d_mats, d_all_pair, 1, inner_sweeps);

@@ -32,6 +32,7 @@ struct GemmPolicy {
   static constexpr int BN = TBN;
   static constexpr bool B_IS_A = false;
   static constexpr uint32_t TX_BYTES = 2 * tc::PTILE;
+  static constexpr bool MN_MAJOR = false;
 
   __device__ static bool decode(const Params& p, int w, Item& it) {
     const int tile = w / p.splits, sp = w % p.splits;

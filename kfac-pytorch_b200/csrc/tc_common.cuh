@@ -119,10 +119,24 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, A/B K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+// MN-major operand tile (the reduction index K runs over smem ROWS): 32-element (128 B)
+// MN atoms x 8 K rows, SWIZZLE_128B.  A {32 (MN), 32 (K)} TMA box lands as 4 such atoms
+// stacked along K (1024 B apart = SBO); boxes for successive MN ranges are 4096 B apart
+// (= LBO).  (cute canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)).)
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;  // LBO: next 32-wide MN atom
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: next group of 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate; mn_major: both operands MN-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool mn_major = false) {
   return (1u << 4)                      // c_format = F32
          | (2u << 7) | (2u << 10)       // a_format = b_format = TF32
+         | (mn_major ? ((1u << 15) | (1u << 16)) : 0u)   // a_major, b_major
          | ((uint32_t)(N >> 3) << 17)   // n_dim
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }

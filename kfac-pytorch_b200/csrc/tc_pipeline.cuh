@@ -18,6 +18,7 @@
 //   static constexpr int BN;             64 or 128 (UMMA N)
 //   static constexpr bool B_IS_A;        B tile aliases the A tile (Gram of one operand)
 //   static constexpr uint32_t TX_BYTES;  bytes landed by load() per stage
+//   static constexpr bool MN_MAJOR;      operands are MN-major tiles (K = smem rows), else K-major
 //   __device__ static bool decode(const Params&, int w, Item&);   false -> item is skipped
 //   __device__ static int  num_kb(const Params&, const Item&);    > 0
 //   __device__ static void load(const Params&, const Item&, int kbi, uint8_t* a, uint8_t* b, uint64_t* bar);
@@ -78,7 +79,7 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(PBM, BN);
+      constexpr uint32_t idesc = make_idesc_tf32(PBM, BN, P::MN_MAJOR);
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         typename P::Item it;
@@ -95,13 +96,15 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
         for (int kbi = 0; kbi < nkb; ++kbi) {
           mbar_wait(&conv[s], ph);
           tc_fence_after();
-          const uint64_t ahi = make_kmajor_sw128_desc(smem_u32(tile_ptr(s, 0)));
-          const uint64_t alo = make_kmajor_sw128_desc(smem_u32(tile_ptr(s, 2)));
-          const uint64_t bhi = P::B_IS_A ? ahi : make_kmajor_sw128_desc(smem_u32(tile_ptr(s, 1)));
-          const uint64_t blo = P::B_IS_A ? alo : make_kmajor_sw128_desc(smem_u32(tile_ptr(s, 3)));
+          auto mkdesc = [](uint32_t a) { return P::MN_MAJOR ? make_mnmajor_sw128_desc(a) : make_kmajor_sw128_desc(a); };
+          const uint64_t ahi = mkdesc(smem_u32(tile_ptr(s, 0)));
+          const uint64_t alo = mkdesc(smem_u32(tile_ptr(s, 2)));
+          const uint64_t bhi = P::B_IS_A ? ahi : mkdesc(smem_u32(tile_ptr(s, 1)));
+          const uint64_t blo = P::B_IS_A ? alo : mkdesc(smem_u32(tile_ptr(s, 3)));
 #pragma unroll
           for (int kk = 0; kk < PBK / 8; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);   // 8 fp32 = 32 B = 2 x 16 B units
+            // next 8 reduction indices: 32 B along a K-major row, or 8 rows (1024 B) of an MN-major tile
+            const uint64_t adv = (uint64_t)(P::MN_MAJOR ? kk * 64 : kk * 2);
             mma_tf32(d_corr, alo + adv, bhi + adv, idesc, accum);
             mma_tf32(d_corr, ahi + adv, blo + adv, idesc, 1u);
             mma_tf32(d_main, ahi + adv, bhi + adv, idesc, accum);
