@@ -30,10 +30,10 @@ constexpr int GR = 256;       // rows of G handled per CTA in gram/apply
 constexpr int TC_MIN_N = 768;
 // 1: the Gram reads G itself as an MN-major operand (no transposed copy of G is kept);
 // 0: the Gram reads a K-major G^T that the apply kernel refreshes.
-// (runtime switch for A/B testing: env KFAC_GRAM_KMAJOR=1 selects the G^T variant)
+// (runtime switch: env KFAC_GRAM_MNMAJOR=1 selects the experimental MN-major variant)
 static bool gram_mn_major() {
   static int v = -1;
-  if (v < 0) v = getenv("KFAC_GRAM_KMAJOR") ? 0 : 1;
+  if (v < 0) v = getenv("KFAC_GRAM_MNMAJOR") ? 1 : 0;   // experimental (descriptor not validated): off by default
   return v != 0;
 } // block matrices at least this large use the tcgen05 Gram/apply kernels
 
@@ -414,7 +414,7 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
       const float off = __uint_as_float(mt.sweep_off);
       if (off < mt.tol) mt.done = 1;
       // safety net: stalled at the rounding floor (no longer shrinking, already small)
-      else if (mt.sweeps >= 4 && off < 1e-3f && off > 0.7f * mt.prev_off) mt.done = 1;
+      else if (mt.sweeps >= 4 && off < 10.f * mt.tol && off > 0.9f * mt.prev_off) mt.done = 1;
       mt.prev_off = off;
       mt.sweep_off = 0u;
     }
@@ -632,8 +632,8 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     set_error("eigh: workspace too small (%zu < %zu)", ws_bytes, pl.total);
     return KFAC_ERR_WORKSPACE;
   }
-  if (max_sweeps <= 0) max_sweeps = 30;
-  const int inner_sweeps = 2;   // per block pair and round; the outer sweeps finish the job
+  if (max_sweeps <= 0) max_sweeps = 40;
+  const int inner_sweeps = 4;   // per block pair and round (early exit when nothing rotates)
   char* base = (char*)ws;
   for (int i = 0; i < count; ++i) {
     EighMat& m = pl.mats[i];
