@@ -449,6 +449,31 @@ class BaseKFACPreconditioner:
         if not self._factors_dirty:
             return
         self._factors_dirty = False
+        from kfac_b200.distributed import get_world_size
+        if get_world_size() == 1:
+            return
+        ll = self._layer_list()
+        if ll and ll[0][1].symmetry_aware:
+            # communicate only the upper triangles (kfac/distributed.py:422-465):
+            # pack -> one all-reduce of the packed arena -> mirror back
+            lib = _cabi.load()
+            stream = _cabi.stream_ptr()
+            if getattr(self, '_packed_arena', None) is None:
+                total = sum(l.a_dim * (l.a_dim + 1) // 2 + l.g_dim * (l.g_dim + 1) // 2 for _, l in ll)
+                self._packed_arena = torch.empty(total, dtype=torch.float32, device=self._device)
+            off = 0
+            todo = []
+            for _, l in ll:
+                for view, d in ((l._a_view, l.a_dim), (l._g_view, l.g_dim)):
+                    n = d * (d + 1) // 2
+                    todo.append((view, d, self._packed_arena.narrow(0, off, n)))
+                    off += n
+            for view, d, packed in todo:
+                _cabi.check(lib.kfac_triu_pack(view.data_ptr(), d, packed.data_ptr(), stream), 'kfac_triu_pack')
+            self._tdc.allreduce_average(self._packed_arena, group=None)
+            for view, d, packed in todo:
+                _cabi.check(lib.kfac_triu_unpack(packed.data_ptr(), d, view.data_ptr(), stream), 'kfac_triu_unpack')
+            return
         self._tdc.allreduce_average(self._factor_arena, group=None)
 
     # K5/K6/K7 + C2 -------------------------------------------------------

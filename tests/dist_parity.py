@@ -35,7 +35,7 @@ def main():
     crit = torch.nn.CrossEntropyLoss()
     per_rank = 4
     ok = True
-    for method in ('eigen', 'inverse'):
+    for method, sym in (('eigen', False), ('eigen', True), ('inverse', False)):
         for frac in fracs:
             torch.manual_seed(0)
             ref_model = SmallConvNet()
@@ -44,7 +44,8 @@ def main():
             gx = torch.randn(world * per_rank, 3, 12, 12)
             gy = torch.randint(0, 5, (world * per_rank,))
             x, y = gx[rank * per_rank:(rank + 1) * per_rank].to(dev), gy[rank * per_rank:(rank + 1) * per_rank].to(dev)
-            pre = KFACPreconditioner(model, damping=0.003, grad_worker_fraction=frac, compute_method=method)
+            pre = KFACPreconditioner(model, damping=0.003, grad_worker_fraction=frac, compute_method=method,
+                                     symmetry_aware=sym)
             ref = OraclePreconditioner(ref_model, damping=0.003, compute_method=method) if rank == 0 else None
             worst = 0.0
             for step in range(3):
@@ -73,7 +74,7 @@ def main():
             t = torch.tensor([worst], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
-                print(f'world={world} method={method} grad_worker_fraction={frac:.3f} '
+                print(f'world={world} method={method} symmetry_aware={sym} grad_worker_fraction={frac:.3f} '
                       f'collectives={pre._tdc.calls} worst rel-fro vs oracle = {t.item():.2e}', flush=True)
             ok = ok and t.item() < 1e-3
     dist.barrier()
