@@ -54,6 +54,7 @@ struct alignas(64) EighMat {
   float prev_off;              // convergence measure of the previous sweep
   unsigned int max_diag;       // float bits: largest |g_j|^2 seen (lambda_max^2), atomicMax
   float nw_ratio;              // normwise relaxation, see pair_den()
+  float off_hist[12];          // diagnostics: convergence measure after each of the first sweeps
   int done;
   int sweeps;
 };
@@ -412,6 +413,7 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
     if ((round + 1) % (mt.nb - 1) == 0) {
       mt.sweeps += 1;
       const float off = __uint_as_float(mt.sweep_off);
+      if (mt.sweeps <= 12) mt.off_hist[mt.sweeps - 1] = off;
       if (off < mt.tol) mt.done = 1;
       // safety net: stalled at the rounding floor (no longer shrinking, already small)
       else if (mt.sweeps >= 4 && off < 10.f * mt.tol && off > 0.9f * mt.prev_off) mt.done = 1;
@@ -794,8 +796,12 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
       KFAC_CUDA(cudaMemcpy(back.data(), d_mats, sizeof(EighMat) * count, cudaMemcpyDeviceToHost));
       for (int i = 0; i < count; ++i)
         if (back[i].mode >= 2)
-          fprintf(stderr, "[kfac eigh] n=%d mode=%d warm=%d sweeps=%d done=%d last_off=%.2e\n", back[i].n,
-                  back[i].mode, back[i].V0T != nullptr, back[i].sweeps, back[i].done, back[i].prev_off);
+        {
+          fprintf(stderr, "[kfac eigh] n=%d mode=%d warm=%d sweeps=%d done=%d off:", back[i].n, back[i].mode,
+                  back[i].V0T != nullptr, back[i].sweeps, back[i].done);
+          for (int k = 0; k < back[i].sweeps && k < 12; ++k) fprintf(stderr, " %.1e", back[i].off_hist[k]);
+          fprintf(stderr, "\n");
+        }
     }
   }
   return KFAC_OK;

@@ -5,7 +5,8 @@
 Every rank runs kfac_b200 on its own shard of a global batch; the result must
 equal the single-process CPU oracle on the CONCATENATED batch (for a model
 without BatchNorm, averaging per-rank covariances / gradients is exactly the
-covariance / gradient of the concatenated batch).  Checks every
+covariance / gradient of the concatenated batch once the loss scaling of the
+per-rank mean losses is reproduced).  Checks every
 grad_worker_fraction the world size admits (COMM-OPT, HYBRID-OPT, MEM-OPT).
 """
 import copy
@@ -57,8 +58,14 @@ def main():
                 pre.step()
                 torch.cuda.synchronize()
                 if rank == 0:
+                    # every rank back-propagates the MEAN loss of its own shard, so the
+                    # grad-outputs the G hooks see are 1/per_rank-scaled: reproduce that on the
+                    # concatenated batch with world * mean-loss, then undo the factor on the
+                    # parameter gradients (DDP averages them).
                     ref_model.zero_grad()
-                    crit(ref_model(gx), gy).backward()
+                    (crit(ref_model(gx), gy) * world).backward()
+                    for q in ref_model.parameters():
+                        q.grad /= world
                     ref.step()
                 for i, (p, q) in enumerate(zip(model.parameters(), ref_model.parameters())):
                     want = q.grad.to(dev) if rank == 0 else torch.empty_like(p.grad)
