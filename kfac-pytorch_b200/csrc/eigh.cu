@@ -701,15 +701,32 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     KFAC_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
     attr_set = true;
   }
+  const int nblock = (int)pl.block_list.size();
+  // The small (n <= 128) matrices are solved by single latency-bound CTAs: run them on a
+  // side stream so they overlap with the block-Jacobi rounds of the larger matrices.
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const bool have_direct = !pl.d64_list.empty() || !pl.d128_list.empty();
+  cudaStream_t ds = s;
+  if (have_direct && nblock > 0) {
+    if (!side) {
+      KFAC_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      KFAC_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      KFAC_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    KFAC_CUDA(cudaEventRecord(ev_fork, s));          // descriptors are uploaded on s
+    KFAC_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    ds = side;
+  }
   if (!pl.d64_list.empty()) {
-    jacobi_smem_kernel<64><<<(int)pl.d64_list.size(), 256, smem64, s>>>(d_mats, d_d64, 0, 24);
+    jacobi_smem_kernel<64><<<(int)pl.d64_list.size(), 256, smem64, ds>>>(d_mats, d_d64, 0, 24);
     KFAC_LAUNCH_CHECK();
   }
   if (!pl.d128_list.empty()) {
-    jacobi_smem_kernel<128><<<(int)pl.d128_list.size(), 512, smem128, s>>>(d_mats, d_d128, 0, 24);
+    jacobi_smem_kernel<128><<<(int)pl.d128_list.size(), 512, smem128, ds>>>(d_mats, d_d128, 0, 24);
     KFAC_LAUNCH_CHECK();
   }
-  const int nblock = (int)pl.block_list.size();
+  if (ds != s) KFAC_CUDA(cudaEventRecord(ev_join, side));
   if (nblock > 0) {
     eigh_init_kernel<<<dim3(256, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();
@@ -790,6 +807,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     }
     eigh_final_kernel<<<dim3(64, nblock), 256, 0, s>>>(d_mats, d_block);
     KFAC_LAUNCH_CHECK();
+    if (ds != s) KFAC_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     if (getenv("KFAC_EIGH_DEBUG")) {   // diagnostics only: per-matrix sweep counts (synchronises)
       std::vector<EighMat> back(count);
       KFAC_CUDA(cudaStreamSynchronize(s));
