@@ -57,8 +57,13 @@ long long kfac_launch_count(void);
 /* replaces LinearModuleHelper.get_a_factor / get_g_factor
  * (kfac/layers/modules.py:123-141) + append_bias_ones (utils.py:8-15):
  * x is (rows, features) row-major; d = features + append_ones. */
+/* ws may be NULL (SIMT kernel).  With a workspace of kfac_factor_linear_workspace_bytes()
+ * (non-zero for tall inputs: rows >= 512, features >= 128) the activations are transposed
+ * once into a feature-major matrix and the SYRK runs on the tcgen05 engine. */
+size_t kfac_factor_linear_workspace_bytes(int64_t rows, int features, int append_ones);
 int kfac_factor_linear(const void* x, int dtype, int64_t rows, int features,
-                       int append_ones, float scale, float* acc, void* stream);
+                       int append_ones, float scale, float* acc, void* ws,
+                       size_t ws_bytes, void* stream);
 
 /* replaces Conv2dModuleHelper._extract_patches + get_a_factor
  * (kfac/layers/modules.py:170-178,210-237).  x is NCHW; feature order

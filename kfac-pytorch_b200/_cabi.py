@@ -53,7 +53,8 @@ SIGNATURES = {
     'kfac_last_error': (C.c_char_p, []),
     'kfac_device_arch': (c_int, []),
     'kfac_launch_count': (C.c_longlong, []),
-    'kfac_factor_linear': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'kfac_factor_linear_workspace_bytes': (c_size_t, [c_int64, c_int, c_int]),
+    'kfac_factor_linear': (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     'kfac_factor_conv2d_input_workspace_bytes': (c_size_t, [c_int] * 11),
     'kfac_factor_conv2d_input': (c_int, [c_void_p, c_int] + [c_int] * 11 + [c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     'kfac_factor_conv2d_gradout': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),

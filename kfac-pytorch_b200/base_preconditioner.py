@@ -190,7 +190,8 @@ class BaseKFACPreconditioner:
         # native-side state
         self._arenas_ready = False
         self._device: torch.device | None = None
-        self._scratch = _Scratch()          # im2col
+        self._scratch = _Scratch()          # im2col / transposes (forward hooks)
+        self._scratch_bwd = _Scratch()      # transposes (backward hooks, autograd thread)
         self._eig_scratch = _Scratch()      # eigensolver workspace
         self._gemm_scratch = _Scratch()     # precondition / inverse temporaries
         self._factors_dirty = False
@@ -383,7 +384,8 @@ class BaseKFACPreconditioner:
         self._ensure_arenas(g.device)
         if layer._g_pending:
             self._flush_factor_updates()
-        layer.module.accumulate_g(g, layer._g_batch_view, self._grad_scale_value(layer))
+        # the backward hook runs on the autograd thread: it gets its own scratch buffer
+        layer.module.accumulate_g(g, layer._g_batch_view, self._grad_scale_value(layer), self._scratch_bwd)
         layer._g_count += 1
         if self._update_factors_in_hook and self._mini_steps[name] % self._accumulation_steps == 0:
             self._mark_pending(layer, 'g')

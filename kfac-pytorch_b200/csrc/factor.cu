@@ -163,6 +163,29 @@ __global__ void im2col_kernel(Im2colArgs a) {
   }
 }
 
+// X (rows x feat, sample-major, any dtype) -> out (feat [+1 ones row]) x ld, feature-major fp32
+template <typename T>
+__global__ void to_feature_major_kernel(const void* xin, int64_t rows, int feat, int ones, float* out, int64_t ld) {
+  __shared__ float tile[32][33];
+  const T* __restrict__ x = reinterpret_cast<const T*>(xin);
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int f0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int f = f0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && f < feat) ? to_float<T>(x[r * feat + f]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int f = f0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (r < ld) {
+      if (f < feat) out[(int64_t)f * ld + r] = tile[threadIdx.x][i];
+      else if (f == feat && ones) out[(int64_t)f * ld + r] = (r < rows) ? 1.f : 0.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ EMA
 struct EmaBatch { kfac_ema_item it[48]; int count; float alpha; };
 __global__ void ema_kernel(EmaBatch eb) {
@@ -230,10 +253,35 @@ static inline int grid_for(int64_t total, int threads = 256) {
 
 using namespace kfac;
 
+extern "C" size_t kfac_factor_linear_workspace_bytes(int64_t rows, int features, int append_ones) {
+  if (rows < 512 || features < 128) return 0;   // small problems stay on the SIMT kernel
+  const int64_t ld = (rows + 3) / 4 * 4;
+  return (size_t)ld * (size_t)(features + (append_ones ? 1 : 0)) * sizeof(float);
+}
+
 extern "C" int kfac_factor_linear(const void* x, int dtype, int64_t rows, int features,
-                                  int append_ones, float scale, float* acc, void* stream) {
+                                  int append_ones, float scale, float* acc, void* ws, size_t ws_bytes,
+                                  void* stream) {
   KFAC_CHECK_ARG(x && acc, "null pointer");
   KFAC_CHECK_ARG(rows >= 0 && rows < (1ll << 31) && features > 0, "dims");
+  const size_t need = kfac_factor_linear_workspace_bytes(rows, features, append_ones);
+  if (need > 0 && ws && ws_bytes >= need) {
+    // tall activations (tokens x hidden): transpose once into a feature-major matrix
+    // (ones row materialised) and run the tcgen05 SYRK on it
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ld = (rows + 3) / 4 * 4;
+    const int ones = append_ones ? 1 : 0;
+    dim3 grid(ceil_div(ld, 32), ceil_div(features + ones, 32));
+    if (dtype == KFAC_F32) to_feature_major_kernel<float><<<grid, dim3(32, 8), 0, st>>>(x, rows, features, ones, (float*)ws, ld);
+    else if (dtype == KFAC_F16) to_feature_major_kernel<__half><<<grid, dim3(32, 8), 0, st>>>(x, rows, features, ones, (float*)ws, ld);
+    else if (dtype == KFAC_BF16) to_feature_major_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>(x, rows, features, ones, (float*)ws, ld);
+    else { set_error("unknown dtype %d", dtype); return KFAC_ERR_BAD_ARG; }
+    KFAC_LAUNCH_CHECK();
+    CovArgs a{};
+    a.x = ws; a.ld = ld; a.batch_stride = 0; a.rows = (int)rows; a.batch = 1;
+    a.feat = features + ones; a.ones = 0; a.scale = scale; a.acc = acc;
+    return launch_cov<true>(a, KFAC_F32, st);
+  }
   CovArgs a{};
   a.x = x; a.ld = features; a.batch_stride = 0; a.rows = (int)rows; a.batch = 1;
   a.feat = features; a.ones = append_ones ? 1 : 0; a.scale = scale; a.acc = acc;

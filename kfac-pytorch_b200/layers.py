@@ -62,7 +62,7 @@ class ModuleHelper:
     def accumulate_a(self, x: torch.Tensor, acc: torch.Tensor, scratch) -> None:
         raise NotImplementedError
 
-    def accumulate_g(self, g: torch.Tensor, acc: torch.Tensor, grad_scale: float) -> None:
+    def accumulate_g(self, g: torch.Tensor, acc: torch.Tensor, grad_scale: float, scratch=None) -> None:
         raise NotImplementedError
 
 
@@ -93,19 +93,25 @@ class LinearModuleHelper(ModuleHelper):
         feat = x.size(-1)
         rows = x.numel() // feat
         lib = _cabi.load()
+        need = lib.kfac_factor_linear_workspace_bytes(rows, feat, int(self.has_bias()))
+        ws = scratch.get(need, x.device) if need else None
         _cabi.check(lib.kfac_factor_linear(x.data_ptr(), _dtype_code(x), rows, feat,
                                            int(self.has_bias()), 1.0 / rows, acc.data_ptr(),
+                                           ws.data_ptr() if ws is not None else None, need,
                                            _cabi.stream_ptr()), 'kfac_factor_linear')
 
-    def accumulate_g(self, g, acc, grad_scale):
+    def accumulate_g(self, g, acc, grad_scale, scratch=None):
         _cabi.require_device(g)
         g = g.detach()
         g = g if g.is_contiguous() else g.contiguous()
         feat = g.size(-1)
         rows = g.numel() // feat
         lib = _cabi.load()
+        need = lib.kfac_factor_linear_workspace_bytes(rows, feat, 0) if scratch is not None else 0
+        ws = scratch.get(need, g.device) if need else None
         _cabi.check(lib.kfac_factor_linear(g.data_ptr(), _dtype_code(g), rows, feat, 0,
                                            1.0 / (rows * grad_scale * grad_scale), acc.data_ptr(),
+                                           ws.data_ptr() if ws is not None else None, need,
                                            _cabi.stream_ptr()), 'kfac_factor_linear')
 
 
@@ -150,7 +156,7 @@ class Conv2dModuleHelper(ModuleHelper):
             x.data_ptr(), _dtype_code(x), *geo, ones, scale, acc.data_ptr(),
             ws.data_ptr() if need else None, need, _cabi.stream_ptr()), 'kfac_factor_conv2d_input')
 
-    def accumulate_g(self, g, acc, grad_scale):
+    def accumulate_g(self, g, acc, grad_scale, scratch=None):
         _cabi.require_device(g)
         g = g.detach()
         g = g if g.is_contiguous() else g.contiguous()

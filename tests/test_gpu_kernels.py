@@ -51,7 +51,9 @@ def test_gemm_f32(lib, dev, M, N, K, ta, tb):
 
 @pytest.mark.parametrize('rows,feat,ones,dtype', [(1, 3, 1, torch.float32), (4, 10, 0, torch.float32), (33, 21, 1, torch.float32),
                                                    (1000, 65, 1, torch.float32), (5000, 130, 0, torch.float32),
-                                                   (257, 64, 1, torch.bfloat16), (257, 64, 0, torch.float16)])
+                                                   (257, 64, 1, torch.bfloat16), (257, 64, 0, torch.float16),
+                                                   (2048, 768, 1, torch.float32), (1030, 130, 0, torch.float32),
+                                                   (4096, 256, 1, torch.bfloat16)])
 def test_factor_linear(lib, dev, rows, feat, ones, dtype):
     from oracle import kfac_oracle as O
     torch.manual_seed(rows + feat)
@@ -59,8 +61,11 @@ def test_factor_linear(lib, dev, rows, feat, ones, dtype):
     d = feat + ones
     acc = torch.zeros(d, d, device=dev)
     xd = x.to(dev)
+    need = lib.kfac_factor_linear_workspace_bytes(rows, feat, ones)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
     assert lib.kfac_factor_linear(xd.data_ptr(), {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[dtype],
-                                  rows, feat, ones, 1.0 / rows, acc.data_ptr(), S()) == 0
+                                  rows, feat, ones, 1.0 / rows, acc.data_ptr(), ws.data_ptr() if need else None, need,
+                                  S()) == 0
     torch.cuda.synchronize()
     ref = O.linear_a_factor(x.float(), bool(ones))
     got = 0.5 * (acc + acc.t())
@@ -72,7 +77,7 @@ def test_get_cov_reference_vector_on_gpu(lib, dev):
     # exact vector of the reference's tests/layers/utils_test.py
     a = torch.tensor([[1., 2, 3], [4, 5, 6], [7, 8, 9]], device=dev)
     acc = torch.zeros(3, 3, device=dev)
-    assert lib.kfac_factor_linear(a.data_ptr(), 0, 3, 3, 0, 1.0 / 3, acc.data_ptr(), S()) == 0
+    assert lib.kfac_factor_linear(a.data_ptr(), 0, 3, 3, 0, 1.0 / 3, acc.data_ptr(), None, 0, S()) == 0
     torch.cuda.synchronize()
     assert torch.allclose(acc.cpu(), torch.tensor([[22., 26, 30], [26, 31, 36], [30, 36, 42]]), rtol=1e-6)
 
