@@ -54,6 +54,7 @@ struct alignas(64) EighMat {
   float prev_off;              // convergence measure of the previous sweep
   unsigned int max_diag;       // float bits: largest |g_j|^2 seen (lambda_max^2), atomicMax
   float nw_ratio;              // normwise relaxation, see pair_den()
+  float conv_tol;              // matrix is done when a sweep STARTS below this (>= tol)
   float off_hist[12];          // diagnostics: convergence measure after each of the first sweeps
   int done;
   int sweeps;
@@ -414,7 +415,10 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
       mt.sweeps += 1;
       const float off = __uint_as_float(mt.sweep_off);
       if (mt.sweeps <= 12) mt.off_hist[mt.sweeps - 1] = off;
-      if (off < mt.tol) mt.done = 1;
+      // `off` is measured BEFORE this sweep's rotations; every pair above tol has just been
+      // re-diagonalised, so a sweep that started below conv_tol ends at the rounding floor
+      // (quadratic convergence) -- no verification sweep needed.
+      if (off < mt.conv_tol) mt.done = 1;
       // safety net: stalled at the rounding floor (no longer shrinking, already small)
       else if (mt.sweeps >= 4 && off < 10.f * mt.tol && off > 0.9f * mt.prev_off) mt.done = 1;
       mt.prev_off = off;
@@ -642,7 +646,8 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     m.F = items[i].F; m.Q = items[i].Q; m.QT = items[i].QT; m.d = items[i].d;
     m.V0T = (m.mode >= 2) ? items[i].V0T : nullptr;
     m.ldq = items[i].ldq > 0 ? items[i].ldq : items[i].n;
-    m.tol = tol > 0.f ? tol : 2e-6f;   // residual eigenvector contamination (see rel_off)
+    m.tol = tol > 0.f ? tol : 3e-6f;   // pairs above this are re-diagonalised (see rel_off); ~ fp32 Gram noise floor
+    m.conv_tol = fmaxf(m.tol, tol > 0.f ? tol : 1e-5f);
     m.nw_ratio = (3e-6f / sqrtf((float)m.n)) / m.tol;
     if (m.mode >= 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
