@@ -443,6 +443,8 @@ struct GramPolicyT {
   static constexpr int BN = 128;
   static constexpr bool B_IS_A = true;
   static constexpr bool MN_MAJOR = MN;
+  static constexpr int CHUNK = 1;
+  __device__ static void reset(Item&) {}
   static constexpr uint32_t TX_BYTES = tc::PTILE;
   __device__ static bool decode(const Params& p, int w, Item& it) {
     const int gi = w / p.ksplits, sp = w % p.ksplits;
@@ -486,23 +488,35 @@ struct GramPolicyT {
 struct ApplyParams { EighMat* mats; const int* pair_mat; int max_tiles; int round; };
 struct ApplyPolicy {
   using Params = ApplyParams;
-  struct Item { EighMat* mt; int local, I, J, m0, which; };
+  // pair-level state (pr .. Gt) is cached in the Item: consecutive work items of a CTA
+  // belong to the same pair, so the dependent global loads happen once per pair, not per tile
+  struct Item { EighMat* mt; int local, I, J, m0, which; int pr, active, n, np; float* G; float* V; float* Gt; };
   static constexpr int BN = 64;
   static constexpr bool B_IS_A = false;
   static constexpr bool MN_MAJOR = false;
+  static constexpr int CHUNK = 16;
   static constexpr uint32_t TX_BYTES = tc::PTILE + 64 * 32 * 4;
+  __device__ static void reset(Item& it) { it.pr = -1; it.active = 0; }
   __device__ static bool decode(const Params& p, int w, Item& it) {
     it.which = w & 1;
     const int t = (w >> 1) % p.max_tiles, pr = (w >> 1) / p.max_tiles;
-    EighMat* mt = &p.mats[p.pair_mat[pr]];
-    if (mt->done) return false;
-    it.mt = mt;
-    it.local = pr - mt->pair_base;
-    if (mt->pair_skip[it.local]) return false;
+    if (pr != it.pr) {
+      it.pr = pr;
+      EighMat* mt = &p.mats[p.pair_mat[pr]];
+      it.mt = mt;
+      it.active = 0;
+      if (!mt->done) {
+        it.local = pr - mt->pair_base;
+        if (!mt->pair_skip[it.local]) {
+          it.active = 1;
+          it.n = mt->n; it.np = mt->np; it.G = mt->G; it.V = mt->V; it.Gt = mt->Gt;
+          tournament(p.round % (mt->nb - 1), it.local, mt->nb, it.I, it.J);
+        }
+      }
+    }
+    if (!it.active) return false;
     it.m0 = t * 128;
-    if (it.m0 >= mt->n) return false;
-    tournament(p.round % (mt->nb - 1), it.local, mt->nb, it.I, it.J);
-    return true;
+    return it.m0 < it.n;
   }
   __device__ static int num_kb(const Params&, const Item&) { return 2; }
   __device__ static void load(const Params&, const Item& it, int kbi, uint8_t* a, uint8_t* b, uint64_t* bar) {
@@ -511,13 +525,13 @@ struct ApplyPolicy {
   }
   __device__ static void store(const Params&, const Item& it, int row, int col0, float (&v)[32]) {
     const int r = it.m0 + row;
-    if (r >= it.mt->n) return;
-    const int np = it.mt->np, cb = (col0 == 0 ? it.I : it.J) * JB;
-    float* X = (it.which ? it.mt->V : it.mt->G) + (int64_t)r * np + cb;
+    if (r >= it.n) return;
+    const int np = it.np, cb = (col0 == 0 ? it.I : it.J) * JB;
+    float* X = (it.which ? it.V : it.G) + (int64_t)r * np + cb;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(X + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    if (!it.which && it.mt->Gt) {
-      float* T = it.mt->Gt + (int64_t)cb * np + r;   // lanes hold consecutive rows r: coalesced columns of G^T
+    if (!it.which && it.Gt) {
+      float* T = it.Gt + (int64_t)cb * np + r;   // lanes hold consecutive rows r: coalesced columns of G^T
 #pragma unroll
       for (int j = 0; j < 32; ++j) T[(int64_t)j * np] = v[j];
     }

@@ -33,6 +33,8 @@ struct GemmPolicy {
   static constexpr bool B_IS_A = false;
   static constexpr uint32_t TX_BYTES = 2 * tc::PTILE;
   static constexpr bool MN_MAJOR = false;
+  static constexpr int CHUNK = 1;
+  __device__ static void reset(Item&) {}
 
   __device__ static bool decode(const Params& p, int w, Item& it) {
     const int tile = w / p.splits, sp = w % p.splits;

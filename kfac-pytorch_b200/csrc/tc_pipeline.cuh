@@ -19,7 +19,10 @@
 //   static constexpr bool B_IS_A;        B tile aliases the A tile (Gram of one operand)
 //   static constexpr uint32_t TX_BYTES;  bytes landed by load() per stage
 //   static constexpr bool MN_MAJOR;      operands are MN-major tiles (K = smem rows), else K-major
-//   __device__ static bool decode(const Params&, int w, Item&);   false -> item is skipped
+//   static constexpr int CHUNK;          consecutive items per CTA (lets decode() cache shared state in Item)
+//   __device__ static void reset(Item&);                          called once per role before the loop
+//   __device__ static bool decode(const Params&, int w, Item&);   false -> item is skipped; Item persists
+//                                                                 across calls (may cache)
 //   __device__ static int  num_kb(const Params&, const Item&);    > 0
 //   __device__ static void load(const Params&, const Item&, int kbi, uint8_t* a, uint8_t* b, uint64_t* bar);
 //   __device__ static void store(const Params&, const Item&, int row, int col0, float (&v)[32]);
@@ -48,6 +51,7 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   constexpr int BN = P::BN;
+  constexpr int CH = P::CHUNK;   // consecutive work items handled by one CTA (decode amortisation)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -65,8 +69,10 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        typename P::Item it;
+      typename P::Item it;
+      P::reset(it);
+      for (int wb = blockIdx.x * CH; wb < total_work; wb += gridDim.x * CH)
+      for (int w = wb; w < min(wb + CH, total_work); ++w) {
         if (!P::decode(p, w, it)) continue;
         const int nkb = P::num_kb(p, it);
         for (int kbi = 0; kbi < nkb; ++kbi) {
@@ -81,8 +87,10 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(PBM, BN, P::MN_MAJOR);
       int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        typename P::Item it;
+      typename P::Item it;
+      P::reset(it);
+      for (int wb = blockIdx.x * CH; wb < total_work; wb += gridDim.x * CH)
+      for (int w = wb; w < min(wb + CH, total_work); ++w) {
         if (!P::decode(p, w, it)) continue;
         const int nkb = P::num_kb(p, it);
         mbar_wait(&tempty[acc], aph ^ 1);
@@ -120,8 +128,10 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
   } else if (warp < 6) {
     const int t = threadIdx.x - 64;
     int s = 0; uint32_t ph = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      typename P::Item it;
+    typename P::Item it;
+    P::reset(it);
+    for (int wb = blockIdx.x * CH; wb < total_work; wb += gridDim.x * CH)
+    for (int w = wb; w < min(wb + CH, total_work); ++w) {
       if (!P::decode(p, w, it)) continue;
       const int nkb = P::num_kb(p, it);
       for (int kbi = 0; kbi < nkb; ++kbi) {
@@ -151,8 +161,10 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
   } else {
     const int q = warp & 3;
     int acc = 0; uint32_t aph = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      typename P::Item it;
+    typename P::Item it;
+    P::reset(it);
+    for (int wb = blockIdx.x * CH; wb < total_work; wb += gridDim.x * CH)
+    for (int w = wb; w < min(wb + CH, total_work); ++w) {
       if (!P::decode(p, w, it)) continue;
       mbar_wait(&tfull[acc], aph);
       tc_fence_after();
