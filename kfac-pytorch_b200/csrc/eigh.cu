@@ -55,6 +55,9 @@ struct alignas(64) EighMat {
   unsigned int max_diag;       // float bits: largest |g_j|^2 seen (lambda_max^2), atomicMax
   float nw_ratio;              // normwise relaxation, see pair_den()
   float conv_tol;              // matrix is done when a sweep STARTS below this (>= tol)
+  float sweep_sumsq;           // sum over column pairs of rel_off^2 in this sweep (atomicAdd)
+  float rms_tol;               // ... or when sqrt(2*sumsq/n) starts below this
+  float rms_hist[12];
   float off_hist[12];          // diagnostics: convergence measure after each of the first sweeps
   int done;
   int sweeps;
@@ -111,7 +114,7 @@ __global__ void eigh_init_kernel(EighMat* mats, const int* block_list) {
       mt.V[idx] = (i == j) ? 1.f : 0.f;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; mt.prev_off = 1e30f; mt.max_diag = 0u; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { mt.sweep_off = 0u; mt.done = 0; mt.sweeps = 0; mt.prev_off = 1e30f; mt.max_diag = 0u; mt.sweep_sumsq = 0.f; }
 }
 
 __global__ void eigh_final_kernel(EighMat* mats, const int* block_list) {
@@ -244,11 +247,18 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
     if (dmax > 0.f) atomicMax(&mt.max_diag, __float_as_uint(dmax));
     const float max_diag = __uint_as_float(mt.max_diag);   // running maximum over all rounds
     const float nw_ratio = mt.nw_ratio;
-    float mx = 0.f;
+    float mx = 0.f, ss = 0.f;
     for (int idx = tid; idx < N * N; idx += T) {
       const int i = idx / N, j = idx % N;
-      if (j > i) mx = fmaxf(mx, rel_off(M[i][j], M[i][i], M[j][j], max_diag, nw_ratio));
+      if (j > i) {
+        const float r = rel_off(M[i][j], M[i][i], M[j][j], max_diag, nw_ratio);
+        mx = fmaxf(mx, r);
+        ss = fmaf(fminf(r, 1.f), fminf(r, 1.f), ss);
+      }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((tid & 31) == 0 && ss > 0.f) atomicAdd(&mt.sweep_sumsq, ss);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((tid & 31) == 0) redmax[tid >> 5] = mx;
@@ -414,7 +424,13 @@ __global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock
     if ((round + 1) % (mt.nb - 1) == 0) {
       mt.sweeps += 1;
       const float off = __uint_as_float(mt.sweep_off);
-      if (mt.sweeps <= 12) mt.off_hist[mt.sweeps - 1] = off;
+      // root-mean-square contamination per eigenvector: the error of the preconditioned
+      // gradient follows this, not the single worst pair.  (Within-block pairs are seen in
+      // every round of the sweep: divide their share out approximately with nb - 1.)
+      const float rms = sqrtf(2.f * mt.sweep_sumsq / (float)mt.n);
+      if (mt.sweeps <= 12) { mt.off_hist[mt.sweeps - 1] = off; mt.rms_hist[mt.sweeps - 1] = rms; }
+      if (rms < mt.rms_tol) mt.done = 1;
+      mt.sweep_sumsq = 0.f;
       // `off` is measured BEFORE this sweep's rotations; every pair above tol has just been
       // re-diagonalised, so a sweep that started below conv_tol ends at the rounding floor
       // (quadratic convergence) -- no verification sweep needed.
@@ -662,6 +678,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
     m.ldq = items[i].ldq > 0 ? items[i].ldq : items[i].n;
     m.tol = tol > 0.f ? tol : 3e-6f;   // pairs above this are re-diagonalised (see rel_off); ~ fp32 Gram noise floor
     m.conv_tol = fmaxf(m.tol, tol > 0.f ? tol : 1e-5f);
+    m.rms_tol = tol > 0.f ? tol : 2e-5f;
     m.nw_ratio = (3e-6f / sqrtf((float)m.n)) / m.tol;
     if (m.mode >= 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
@@ -836,7 +853,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
         {
           fprintf(stderr, "[kfac eigh] n=%d mode=%d warm=%d sweeps=%d done=%d off:", back[i].n, back[i].mode,
                   back[i].V0T != nullptr, back[i].sweeps, back[i].done);
-          for (int k = 0; k < back[i].sweeps && k < 12; ++k) fprintf(stderr, " %.1e", back[i].off_hist[k]);
+          for (int k = 0; k < back[i].sweeps && k < 12; ++k) fprintf(stderr, " %.1e/%.1e", back[i].off_hist[k], back[i].rms_hist[k]);
           fprintf(stderr, "\n");
         }
     }
