@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(256) eigh_gram_kernel(EighMat* mats, const int
 //                 Q and d written directly.
 template <int N>
 __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const int* list,
-                                                           int mode_block, int max_inner) {
+                                                           int mode_block, int max_inner,
+                                                           int tc_first = 0, int* active_list = nullptr,
+                                                           int* active_count = nullptr) {
   extern __shared__ float sm[];
   float (*M)[N + 1] = reinterpret_cast<float (*)[N + 1]>(sm);
   float (*W)[N + 1] = reinterpret_cast<float (*)[N + 1]>(sm + N * (N + 1));
@@ -274,6 +276,8 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
     if (tid == 0) {
       atomicMax(&mt.sweep_off, __float_as_uint(mx));
       mt.pair_skip[local] = (mx < tol) ? 1 : 0;
+      // compact list of tensor-core-class pairs that will be applied this round
+      if (!(mx < tol) && mt.mode == 3 && active_list) active_list[atomicAdd(active_count, 1)] = blockIdx.x - tc_first;
     }
     if (mx < tol) return;
   }
@@ -284,6 +288,7 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
   int* pq = reinterpret_cast<int*>(cs + N);   // (p,q) of every pair of the current step
   for (int sweep = 0; sweep < max_inner; ++sweep) {
     int rotated_sweep = 0;
+    int big_rotation = 0;   // some |sin| >= 2e-3 in this sweep
     for (int st = 0; st < N - 1; ++st) {
       int rotated = 0;
       if (tid < N / 2) {
@@ -297,15 +302,17 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
           const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
           c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's bias makes column norms drift
           s = t * c;
-          if (s != 0.f) rotated = 1;
+          if (s != 0.f) rotated = (fabsf(s) >= 2e-3f) ? 3 : 1;
         }
         cs[tid] = c;
         cs[N / 2 + tid] = s;
         pq[tid] = p | (q << 16);
       }
       // barrier + "did anybody rotate": a step without rotations is skipped entirely
-      if (!__syncthreads_or(rotated)) continue;
+      const int any = __syncthreads_or(rotated);
+      if (!any) continue;
       rotated_sweep = 1;
+      big_rotation |= (any & 2);
       // M <- J^T M J on independent 2x2 blocks (pair a rows) x (pair b columns)
       for (int idx = tid; idx < (N / 2) * (N / 2); idx += T) {
         const int b = idx % (N / 2), a = idx / (N / 2);
@@ -332,7 +339,8 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
       }
       __syncthreads();
     }
-    if (!rotated_sweep) break;
+    // all rotations tiny: the next sweep would only find second-order leftovers
+    if (!rotated_sweep || !big_rotation) break;
   }
 
   if (mode_block) {
@@ -416,7 +424,9 @@ __global__ void __launch_bounds__(256) eigh_apply_kernel(EighMat* mats, const in
   }
 }
 
-__global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock, int round, int* all_done) {
+__global__ void eigh_ctl_kernel(EighMat* mats, const int* block_list, int nblock, int round, int* all_done,
+                                int* active_count) {
+  if (threadIdx.x == 0) *active_count = 0;
   int pending = 0;
   for (int i = threadIdx.x; i < nblock; i += blockDim.x) {
     EighMat& mt = mats[block_list[i]];
@@ -461,6 +471,7 @@ struct GramPolicyT {
   static constexpr bool MN_MAJOR = MN;
   static constexpr int CHUNK = 1;
   __device__ static void reset(Item&) {}
+  __device__ static int total_work(const Params&, int t) { return t; }
   static constexpr uint32_t TX_BYTES = tc::PTILE;
   __device__ static bool decode(const Params& p, int w, Item& it) {
     const int gi = w / p.ksplits, sp = w % p.ksplits;
@@ -501,7 +512,9 @@ struct GramPolicyT {
 };
 
 // Apply: X[rows, I u J] <- X[rows, I u J] W for X in {G, V}; G also refreshes G^T.
-struct ApplyParams { EighMat* mats; const int* pair_mat; int max_tiles; int round; };
+// active_list/active_count: tensor-core-class pairs that the shared-memory Jacobi actually
+// rotated this round (compacted on the device), so converged pairs cost nothing here
+struct ApplyParams { EighMat* mats; const int* pair_mat; int max_tiles; int round; const int* active_list; const int* active_count; };
 struct ApplyPolicy {
   using Params = ApplyParams;
   // pair-level state (pr .. Gt) is cached in the Item: consecutive work items of a CTA
@@ -513,22 +526,19 @@ struct ApplyPolicy {
   static constexpr int CHUNK = 16;
   static constexpr uint32_t TX_BYTES = tc::PTILE + 64 * 32 * 4;
   __device__ static void reset(Item& it) { it.pr = -1; it.active = 0; }
+  __device__ static int total_work(const Params& p, int) { return *p.active_count * p.max_tiles * 2; }
   __device__ static bool decode(const Params& p, int w, Item& it) {
     it.which = w & 1;
-    const int t = (w >> 1) % p.max_tiles, pr = (w >> 1) / p.max_tiles;
-    if (pr != it.pr) {
-      it.pr = pr;
+    const int t = (w >> 1) % p.max_tiles, slot = (w >> 1) / p.max_tiles;
+    if (slot != it.pr) {
+      it.pr = slot;
+      const int pr = p.active_list[slot];
       EighMat* mt = &p.mats[p.pair_mat[pr]];
       it.mt = mt;
-      it.active = 0;
-      if (!mt->done) {
-        it.local = pr - mt->pair_base;
-        if (!mt->pair_skip[it.local]) {
-          it.active = 1;
-          it.n = mt->n; it.np = mt->np; it.G = mt->G; it.V = mt->V; it.Gt = mt->Gt;
-          tournament(p.round % (mt->nb - 1), it.local, mt->nb, it.I, it.J);
-        }
-      }
+      it.local = pr - mt->pair_base;
+      it.active = 1;
+      it.n = mt->n; it.np = mt->np; it.G = mt->G; it.V = mt->V; it.Gt = mt->Gt;
+      tournament(p.round % (mt->nb - 1), it.local, mt->nb, it.I, it.J);
     }
     if (!it.active) return false;
     it.m0 = t * 128;
@@ -565,7 +575,7 @@ struct EighPlan {
   std::vector<int> pair_mat, block_list, d64_list, d128_list;
   std::vector<int> tc_pair_mat, tc_gram_mat, simt_list;
   size_t off_mats, off_pair_mat, off_block, off_d64, off_d128, off_flag, off_data, total;
-  size_t off_tc_pair, off_tc_gram, off_simt, off_all_pair;
+  size_t off_tc_pair, off_tc_gram, off_simt, off_all_pair, off_active;
   int total_pairs, max_nb, max_rows;
   int tc_pairs, tc_gram_items, tc_max_rows, simt_max_rows;
 };
@@ -622,6 +632,7 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
     else if (m.mode == 3) m.inner_base = pl.total_pairs + m.pair_base;
   }
   pl.off_flag = take(sizeof(int) * 4);
+  pl.off_active = take(sizeof(int) * std::max<size_t>(1, pl.tc_pair_mat.size()));
   pl.off_all_pair = take(sizeof(int) * std::max<size_t>(1, pl.pair_mat.size() + pl.tc_pair_mat.size()));
   pl.off_tc_pair = take(sizeof(int) * std::max<size_t>(1, pl.tc_pair_mat.size()));
   pl.off_tc_gram = take(sizeof(int) * std::max<size_t>(1, pl.tc_gram_mat.size()));
@@ -795,6 +806,10 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
       apply_total = pl.tc_pairs * ap.max_tiles * 2;
     }
     int* d_flag = (int*)(base + pl.off_flag);
+    int* d_active_count = d_flag + 1;
+    int* d_active_list = (int*)(base + pl.off_active);
+    KFAC_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int) * 4, s));
+    ap.active_list = d_active_list; ap.active_count = d_active_count;
     // Early exit without draining the GPU: the host enqueues sweep s+1, then waits
     // for the "all matrices converged" flag of sweep s (pinned read-back + event).
     static int* h_flag = nullptr;
@@ -820,7 +835,8 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
             tc::pipeline_kernel<GramPolicyT<false>><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
           count_launch(1);
         }
-        jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 256, smem64, s>>>(d_mats, d_all_pair, 1, inner_sweeps);
+        jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 256, smem64, s>>>(d_mats, d_all_pair, 1, inner_sweeps,
+                                                                                 pl.total_pairs, d_active_list, d_active_count);
         count_launch(1);
         if (pl.total_pairs > 0) {
           eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
@@ -830,7 +846,7 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
           tc::pipeline_kernel<ApplyPolicy><<<std::min(apply_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(ap, apply_total);
           count_launch(1);
         }
-        eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r, d_flag);
+        eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r, d_flag, d_active_count);
       }
       KFAC_LAUNCH_CHECK();
       h_flag[sw & 1] = 0;

@@ -35,6 +35,7 @@ struct GemmPolicy {
   static constexpr bool MN_MAJOR = false;
   static constexpr int CHUNK = 1;
   __device__ static void reset(Item&) {}
+  __device__ static int total_work(const Params&, int t) { return t; }
 
   __device__ static bool decode(const Params& p, int w, Item& it) {
     const int tile = w / p.splits, sp = w % p.splits;

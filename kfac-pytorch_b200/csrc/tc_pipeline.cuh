@@ -20,6 +20,7 @@
 //   static constexpr uint32_t TX_BYTES;  bytes landed by load() per stage
 //   static constexpr bool MN_MAJOR;      operands are MN-major tiles (K = smem rows), else K-major
 //   static constexpr int CHUNK;          consecutive items per CTA (lets decode() cache shared state in Item)
+//   __device__ static int  total_work(const Params&, int host_total);   effective number of work items
 //   __device__ static void reset(Item&);                          called once per role before the loop
 //   __device__ static bool decode(const Params&, int w, Item&);   false -> item is skipped; Item persists
 //                                                                 across calls (may cache)
@@ -54,6 +55,7 @@ pipeline_kernel(const __grid_constant__ typename P::Params p, int total_work) {
   constexpr int CH = P::CHUNK;   // consecutive work items handled by one CTA (decode amortisation)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  total_work = P::total_work(p, total_work);   // a policy may shrink the host-side upper bound (device-side work list)
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 4); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
