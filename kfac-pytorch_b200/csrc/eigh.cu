@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
   float (*W)[N + 1] = reinterpret_cast<float (*)[N + 1]>(sm + N * (N + 1));
   float* cs = sm + 2 * N * (N + 1);       // c[N/2], s[N/2]
   __shared__ float redmax[32];
+  __shared__ int sh_big;
   constexpr int T = N * 4;
   const int tid = threadIdx.x;
   EighMat& mt = mats[list[blockIdx.x]];
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
   int* pq = reinterpret_cast<int*>(cs + N);   // (p,q) of every pair of the current step
   for (int sweep = 0; sweep < max_inner; ++sweep) {
     int rotated_sweep = 0;
-    int big_rotation = 0;   // some |sin| >= 2e-3 in this sweep
+    if (tid == 0) sh_big = 0;   // set when some |sin| >= 2e-3 in this sweep
+    __syncthreads();
     for (int st = 0; st < N - 1; ++st) {
       int rotated = 0;
       if (tid < N / 2) {
@@ -302,17 +304,15 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
           const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
           c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's bias makes column norms drift
           s = t * c;
-          if (s != 0.f) rotated = (fabsf(s) >= 2e-3f) ? 3 : 1;
+          if (s != 0.f) { rotated = 1; if (fabsf(s) >= 2e-3f) sh_big = 1; }
         }
         cs[tid] = c;
         cs[N / 2 + tid] = s;
         pq[tid] = p | (q << 16);
       }
       // barrier + "did anybody rotate": a step without rotations is skipped entirely
-      const int any = __syncthreads_or(rotated);
-      if (!any) continue;
+      if (!__syncthreads_or(rotated)) continue;
       rotated_sweep = 1;
-      big_rotation |= (any & 2);
       // M <- J^T M J on independent 2x2 blocks (pair a rows) x (pair b columns)
       for (int idx = tid; idx < (N / 2) * (N / 2); idx += T) {
         const int b = idx % (N / 2), a = idx / (N / 2);
@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
       __syncthreads();
     }
     // all rotations tiny: the next sweep would only find second-order leftovers
-    if (!rotated_sweep || !big_rotation) break;
+    const int big = sh_big;
+    __syncthreads();
+    if (!rotated_sweep || !big) break;
   }
 
   if (mode_block) {
