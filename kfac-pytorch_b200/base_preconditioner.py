@@ -49,16 +49,18 @@ class _Scratch:
 
 
 def _storage_numel(shape: tuple[int, ...]) -> int:
+    """Floats reserved for one arena entry; always a multiple of 4 so that every
+    entry starts 16-byte aligned (TMA / tcgen05 GEMM operands)."""
     if len(shape) == 2:
         return shape[0] * _cabi.ld4(shape[1])
-    return shape[0]
+    return _cabi.ld4(shape[0])
 
 
 def _bind(arena: torch.Tensor, off: int, shape: tuple[int, ...]) -> torch.Tensor:
     """Storage tensor of one arena entry: (rows, ld4(cols)) or (n,)."""
     n = _storage_numel(shape)
     t = arena.narrow(0, off, n)
-    return t.view(shape[0], _cabi.ld4(shape[1])) if len(shape) == 2 else t
+    return t.view(shape[0], _cabi.ld4(shape[1])) if len(shape) == 2 else t.narrow(0, 0, shape[0])
 
 
 class _Segment:
