@@ -259,7 +259,9 @@ class BaseKFACPreconditioner:
         _cabi.load()
         self._device = device
         ll = self._layer_list()
-        total = sum(l.a_dim ** 2 + l.g_dim ** 2 for _, l in ll)
+        # dense d x d factors, each starting 16-byte aligned (they are TMA operands of the
+        # warm-start GEMM G = F V0)
+        total = sum(_cabi.ld4(l.a_dim ** 2) + _cabi.ld4(l.g_dim ** 2) for _, l in ll)
         self._factor_arena = torch.zeros(total, dtype=torch.float32, device=device)
         self._batch_arena = torch.zeros(total, dtype=torch.float32, device=device)
         off = 0
@@ -268,7 +270,7 @@ class BaseKFACPreconditioner:
                 n = dim * dim
                 setattr(l, fa, self._factor_arena.narrow(0, off, n).view(dim, dim))
                 setattr(l, ba, self._batch_arena.narrow(0, off, n).view(dim, dim))
-                off += n
+                off += _cabi.ld4(n)
         # second-order data + preconditioned gradients
         self._inv_segments, self._grad_segments = build_comm_plan(ll, self._assignment)
         inv_total = sum(s.numel for s in self._inv_segments)
