@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) eigh_gram_kernel(EighMat* mats, const int
 // mode_block = 0: blockIdx.x indexes `list`; the matrix itself is solved,
 //                 Q and d written directly.
 template <int N>
-__global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const int* list,
+__global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const int* list,
                                                            int mode_block, int max_inner,
                                                            int tc_first = 0, int* active_list = nullptr,
                                                            int* active_count = nullptr) {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(N * 4) jacobi_smem_kernel(EighMat* mats, const
   float* cs = sm + 2 * N * (N + 1);       // c[N/2], s[N/2]
   __shared__ float redmax[32];
   __shared__ int sh_big;
-  constexpr int T = N * 4;
+  constexpr int T = N * 8;   // 512 / 1024 threads: the 2x2-block update is latency bound, more threads = fewer serial LDS/STS
   const int tid = threadIdx.x;
   EighMat& mt = mats[list[blockIdx.x]];
   int local = 0;
@@ -810,11 +810,11 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     ds = side;
   }
   if (!pl.d64_list.empty()) {
-    jacobi_smem_kernel<64><<<(int)pl.d64_list.size(), 256, SMEM64, ds>>>(d_mats, d_d64, 0, 24);
+    jacobi_smem_kernel<64><<<(int)pl.d64_list.size(), 512, SMEM64, ds>>>(d_mats, d_d64, 0, 24);
     KFAC_LAUNCH_CHECK();
   }
   if (!pl.d128_list.empty()) {
-    jacobi_smem_kernel<128><<<(int)pl.d128_list.size(), 512, SMEM128, ds>>>(d_mats, d_d128, 0, 24);
+    jacobi_smem_kernel<128><<<(int)pl.d128_list.size(), 1024, SMEM128, ds>>>(d_mats, d_d128, 0, 24);
     KFAC_LAUNCH_CHECK();
   }
   if (ds != s) KFAC_CUDA(cudaEventRecord(ev_join, side));
@@ -874,7 +874,7 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
             tc::pipeline_kernel<GramPolicyT<false>><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
           count_launch(1);
         }
-        jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 256, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps,
+        jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps,
                                                                                  pl.total_pairs, d_active_list, d_active_count);
         count_launch(1);
         if (pl.total_pairs > 0) {
