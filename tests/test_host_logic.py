@@ -189,3 +189,20 @@ def test_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, 'ok'), (1, 'ok')], res
+
+
+def test_arena_entries_are_16_byte_aligned():
+    """Every second-order arena entry must start on a multiple of 4 floats: a vector entry of odd
+    length in front of a matrix would break the TMA alignment of everything behind it."""
+    from kfac_b200.base_preconditioner import _storage_numel
+    from kfac_b200.enums import ComputeMethod
+    for method, prediv in ((ComputeMethod.EIGEN, True), (ComputeMethod.EIGEN, False), (ComputeMethod.INVERSE, False)):
+        for a, (inv, grad) in _plans(2, 1.0, method, prediv, True):
+            for segs in (inv, grad):
+                for s in segs:
+                    assert s.offset % 4 == 0 and s.numel % 4 == 0
+                    off = s.offset
+                    for _, _, shape in s.entries:
+                        assert off % 4 == 0, (method, shape)
+                        off += _storage_numel(shape)
+    assert _storage_numel((147,)) == 148 and _storage_numel((10, 21)) == 10 * 24
