@@ -24,8 +24,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import warnings  # noqa: E402
+
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
+
+warnings.filterwarnings('ignore', message='Full backward hook is firing')
 
 METRIC = 'images/sec ResNet-50 K-FAC training step (fwd+bwd+factor hooks+preconditioner.step()+SGD), factor=inv=1'
 
