@@ -157,6 +157,12 @@ typedef struct kfac_precond_item {
   int ldqa, ldqg, ld_dgda;
   float* P; /* out: g x a fp32 (ld = ldp) */
   int ldp;
+  /* fused compute + broadcast (replaces KFACBaseLayer.broadcast_grad, layers/base.py:224-252):
+   * HOST array of n_peers (<= 7) device pointers -- the same P entry inside the peer ranks'
+   * P arenas, mapped with kfac_peer_open().  The epilogue of the last GEMM stores every tile
+   * to P and to all peers (P2P over NVLink).  n_peers = 0: local only. */
+  float* const* peer_P;
+  int n_peers;
 } kfac_precond_item;
 size_t kfac_precondition_workspace_bytes(const kfac_precond_item* items, int count);
 int kfac_precondition(const kfac_precond_item* items, int count, int method,
@@ -182,6 +188,15 @@ int kfac_grad_scale(const kfac_grad_item* items, int count, float kl_clip,
 /* scale may be NULL (no clipping: scale = 1) */
 int kfac_grad_update(const kfac_grad_item* items, int count, const float* scale,
                      void* stream);
+
+/* ---------------------------------------------------------- peer memory
+ * Buffers that other ranks of the node write into directly (CUDA IPC over NVLink).
+ * kfac_peer_alloc: cudaMalloc + zero + export a 64-byte IPC handle (caller-owned: free with
+ * kfac_peer_free).  kfac_peer_open maps a handle exported by ANOTHER process. */
+int kfac_peer_alloc(size_t bytes, void** dev_ptr, void* handle64);
+int kfac_peer_open(const void* handle64, void** dev_ptr);
+int kfac_peer_close(void* dev_ptr);
+int kfac_peer_free(void* dev_ptr);
 
 /* ---------------------------------------------------- communication helpers
  * replaces get_triu / fill_triu (kfac/distributed.py:422-465): pack the upper

@@ -39,7 +39,8 @@ class PrecondItem(C.Structure):
                 ('dgda', c_void_p), ('da', c_void_p), ('dg', c_void_p),
                 ('a_inv', c_void_p), ('g_inv', c_void_p),
                 ('ldqa', c_int), ('ldqg', c_int), ('ld_dgda', c_int),
-                ('P', c_void_p), ('ldp', c_int)]
+                ('P', c_void_p), ('ldp', c_int),
+                ('peer_P', C.POINTER(c_void_p)), ('n_peers', c_int)]
 
 
 class GradItem(C.Structure):
@@ -68,6 +69,10 @@ SIGNATURES = {
     'kfac_precondition': (c_int, [C.POINTER(PrecondItem), c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
     'kfac_grad_scale': (c_int, [C.POINTER(GradItem), c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     'kfac_grad_update': (c_int, [C.POINTER(GradItem), c_int, c_void_p, c_void_p]),
+    'kfac_peer_alloc': (c_int, [c_size_t, C.POINTER(c_void_p), c_void_p]),
+    'kfac_peer_open': (c_int, [c_void_p, C.POINTER(c_void_p)]),
+    'kfac_peer_close': (c_int, [c_void_p]),
+    'kfac_peer_free': (c_int, [c_void_p]),
     'kfac_triu_pack': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'kfac_triu_unpack': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     'kfac_scale_inplace': (c_int, [c_void_p, c_int64, c_float, c_void_p]),

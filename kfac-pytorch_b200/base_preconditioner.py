@@ -202,6 +202,8 @@ class BaseKFACPreconditioner:
         # Jacobi warm start: successive factors differ by one EMA step, so the previous
         # eigenbasis nearly diagonalises the new factor (fewer sweeps, same result)
         self.warm_start = True
+        # store preconditioned gradients straight into the receivers' arenas (P2P) instead of broadcasting
+        self.fused_grad_broadcast = True
         self._have_basis: set[int] = set()
 
         for module in self._layers:
@@ -276,7 +278,8 @@ class BaseKFACPreconditioner:
         inv_total = sum(s.numel for s in self._inv_segments)
         p_total = sum(s.numel for s in self._grad_segments)
         self._inv_arena = torch.zeros(max(inv_total, 1), dtype=torch.float32, device=device)
-        self._p_arena = torch.zeros(max(p_total, 1), dtype=torch.float32, device=device)
+        self._peer_p_bases = None      # rank -> device pointer of that rank's P arena (fused broadcast)
+        self._p_arena = self._alloc_p_arena(max(p_total, 1), device)
         for segs, arena in ((self._inv_segments, self._inv_arena), (self._grad_segments, self._p_arena)):
             for s in segs:
                 off = s.offset
@@ -321,6 +324,53 @@ class BaseKFACPreconditioner:
         self._vg = torch.zeros(1, dtype=torch.float64, device=device)
         self._nu = torch.ones(1, dtype=torch.float32, device=device)
         self._arenas_ready = True
+
+    def _alloc_p_arena(self, numel: int, device: torch.device) -> torch.Tensor:
+        """P arena.  With gradient broadcasts (KAISA HYBRID/MEM-OPT) it is allocated as CUDA-IPC
+        peer memory and mapped into the other ranks of the gradient-receiver group, so the last
+        precondition GEMM can store its tiles straight into every receiver (fused compute +
+        broadcast over NVLink) instead of a broadcast per source afterwards."""
+        import torch.distributed as dist
+        want = (self.fused_grad_broadcast and dist.is_available() and dist.is_initialized()
+                and self._assignment.broadcast_gradients() and self._layers)
+        if want:
+            try:
+                name0 = next(iter(self._layers.values()))[0]
+                group = self._assignment.grad_receiver_group(name0)
+                if dist.get_backend(group) != 'nccl' or dist.get_world_size(group) < 2 \
+                        or dist.get_world_size(group) > 8:
+                    raise RuntimeError('fused broadcast needs an NCCL group of 2..8 ranks')
+                lib = _cabi.load()
+                ptr = C.c_void_p()
+                handle = (C.c_ubyte * 64)()
+                _cabi.check(lib.kfac_peer_alloc(numel * 4, C.byref(ptr), handle), 'kfac_peer_alloc')
+
+                class _Raw:   # zero-copy torch view of the cudaMalloc'ed buffer
+                    pass
+                raw = _Raw()
+                raw.__cuda_array_interface__ = {'shape': (numel,), 'typestr': '<f4', 'data': (ptr.value, False),
+                                                'version': 3, 'strides': None}
+                arena = torch.as_tensor(raw, device=device)
+                me = get_rank()
+                gathered = [None] * dist.get_world_size(group)
+                dist.all_gather_object(gathered, (me, bytes(handle)), group=group)
+                bases = {}
+                for r, h in gathered:
+                    if r == me:
+                        continue
+                    out = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                    _cabi.check(lib.kfac_peer_open(buf, C.byref(out)), 'kfac_peer_open')
+                    bases[r] = out.value
+                self._peer_p_bases = bases
+                self._p_raw = raw
+                self._row_group = group
+                self._row_token = torch.zeros(1, dtype=torch.float32, device=device)
+                return arena
+            except Exception as e:  # noqa: BLE001
+                logger.warning('fused gradient broadcast unavailable (%s); using NCCL broadcasts', e)
+                self._peer_p_bases = None
+        return torch.zeros(numel, dtype=torch.float32, device=device)
 
     # ------------------------------------------------------------ state dict
     def state_dict(self, include_factors: bool = True) -> dict[str, Any]:
@@ -579,6 +629,9 @@ class BaseKFACPreconditioner:
         todo = [(n, l) for n, l in reversed(self._layer_list()) if self._assignment.is_grad_worker(n)]
         eigen = None
         items = (_cabi.PrecondItem * max(1, len(todo)))()
+        fused = self._peer_p_bases is not None
+        peer_arrays = []   # keep the ctypes pointer arrays alive during the call
+        p_base = self._p_arena.data_ptr()
         for i, (name, layer) in enumerate(todo):
             w, b = self._grad_ptrs(layer)
             I = layer._inv
@@ -605,7 +658,16 @@ class BaseKFACPreconditioner:
                 p('qg'), I['_qgT'].data_ptr() if eig_ok else None,
                 p('dgda'), p('da'), p('dg'), p('a_inv'), p('g_inv'),
                 _cabi.ld4(layer.a_dim), _cabi.ld4(layer.g_dim), _cabi.ld4(layer.a_dim),
-                layer._p_store.data_ptr(), _cabi.ld4(layer.a_dim))
+                layer._p_store.data_ptr(), _cabi.ld4(layer.a_dim), None, 0)
+            if fused:
+                off = layer._p_store.data_ptr() - p_base
+                arr = (C.c_void_p * len(self._peer_p_bases))(*[b + off for b in self._peer_p_bases.values()])
+                peer_arrays.append(arr)
+                items[i].peer_P = arr
+                items[i].n_peers = len(self._peer_p_bases)
+        if fused:
+            # nobody may still be reading the previous step's P when the peers start storing
+            self._tdc.fence(self._row_token, group=self._row_group)
         if todo:
             need = lib.kfac_precondition_workspace_bytes(items, len(todo))
             ws = self._gemm_scratch.get(need, self._device)
@@ -613,9 +675,14 @@ class BaseKFACPreconditioner:
                                               float(self.damping), ws.data_ptr(), need, _cabi.stream_ptr()),
                         'kfac_precondition')
         if self._assignment.broadcast_gradients():
-            for seg in self._grad_segments:
-                self._tdc.broadcast(self._p_arena.narrow(0, seg.offset, seg.numel), src=seg.src,
-                                    group=seg.group)
+            if fused:
+                # the tiles are already in every receiver's arena; one tiny collective in the
+                # receiver group orders "all sources have stored" before anyone reads P
+                self._tdc.fence(self._row_token, group=self._row_group)
+            else:
+                for seg in self._grad_segments:
+                    self._tdc.broadcast(self._p_arena.narrow(0, seg.offset, seg.numel), src=seg.src,
+                                        group=seg.group)
         for _, layer in self._layer_list():
             layer._grad_ready = True
 

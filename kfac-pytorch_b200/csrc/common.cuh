@@ -102,6 +102,7 @@ struct TcGemmArgs {
   int splits;                      // <= 0: automatic
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
+  float* peerD[7]; int npeer;      // fused broadcast: the epilogue also stores the tile into these peer copies of D
 };
 bool tc_gemm_supported(const TcGemmArgs& a);
 int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream);

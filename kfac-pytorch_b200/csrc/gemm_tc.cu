@@ -24,6 +24,7 @@ struct TcParams {
   int tiles_m, tiles_n, splits, upper_only, atomic;
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
+  float* peerD[7]; int npeer;
 };
 
 struct GemmPolicy {
@@ -77,6 +78,14 @@ struct GemmPolicy {
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      // fused compute + broadcast: the same tile goes straight to the peers' copies of D
+      // (P2P stores over NVLink, overlapped with the MMAs of the next tile)
+      for (int q = 0; q < p.npeer; ++q) {
+        float* prow = p.peerD[q] + (int64_t)m * p.ldd + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -87,6 +96,7 @@ struct GemmPolicy {
         } else {
           drow[j] = v[j];
           if (mirror) p.D[(int64_t)(nb + j) * p.ldd + m] = v[j];
+          for (int q = 0; q < p.npeer; ++q) p.peerD[q][(int64_t)m * p.ldd + nb + j] = v[j];
         }
       }
     }
@@ -182,6 +192,9 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream) {
   p.tiles_m = ceil_div(a.M, TBM); p.tiles_n = ceil_div(a.N, TBN);
   p.upper_only = a.upper_only; p.atomic = a.atomic; p.alpha = a.alpha;
   p.epi = a.epi; p.E = a.E; p.lde = a.lde; p.dg = a.dg; p.da = a.da; p.damping = a.damping;
+  p.npeer = a.npeer;
+  for (int q = 0; q < a.npeer && q < 7; ++q) p.peerD[q] = a.peerD[q];
+  if (a.npeer > 0 && (a.atomic || a.upper_only)) { set_error("tc_gemm: peer stores need the plain-store epilogue"); return KFAC_ERR_BAD_ARG; }
   const int ntiles = a.upper_only ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
   const int kb_total = ceil_div(a.K, TBK) * kbatch;
   int splits = a.splits;

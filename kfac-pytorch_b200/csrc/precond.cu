@@ -1,5 +1,7 @@
 // K7-K12: damped inverse from the eigendecomposition, two-sided Kronecker
 // precondition, kl-clip scale and in-place gradient write-back.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace kfac {
@@ -101,13 +103,31 @@ struct Epi { int kind = EPI_NONE; const float* E = nullptr; int64_t lde = 0;
 
 // D (M x N, ldd) = epi(A B^T), A (M x K, lda), B (N x K, ldb): tensor-core engine for
 // aligned operands with at least one full tile worth of work, SIMT engine otherwise.
+// row-major (rows x ld) copy of D into the peers' buffers (layers that did not go through
+// the tensor-core epilogue)
+__global__ void peer_scatter_kernel(const float* D, int64_t total, float* p0, float* p1, float* p2, float* p3,
+                                    float* p4, float* p5, float* p6, int npeer) {
+  float* peers[7] = {p0, p1, p2, p3, p4, p5, p6};
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const float v = D[idx];
+    for (int q = 0; q < npeer; ++q) peers[q][idx] = v;
+  }
+}
+
 int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
-            int K, const Epi& e, cudaStream_t s) {
+            int K, const Epi& e, cudaStream_t s, float* const* peers = nullptr, int npeer = 0) {
   TcGemmArgs t{};
+  t.npeer = 0;
   t.A = A; t.lda = lda; t.B = B; t.ldb = ldb; t.D = D; t.ldd = ldd; t.M = M; t.N = N; t.K = K;
   t.kbatch = 1; t.alpha = 1.f; t.splits = 1;
   t.epi = e.kind; t.E = e.E; t.lde = e.lde; t.dg = e.dg; t.da = e.da; t.damping = e.damping;
   if (M >= 64 && N >= 64 && K >= 32 && tc_gemm_supported(t)) {
+    if (npeer > 0) {   // fused broadcast: plain-store epilogue, no split-K
+      t.npeer = npeer;
+      for (int q = 0; q < npeer; ++q) t.peerD[q] = peers[q];
+      return launch_tc_gemm(t, s);
+    }
     if (e.kind == EPI_NONE && K > 1024) {
       // long reductions: split K across CTAs and add the partial tiles with (round-to-
       // nearest) L2 atomics -- the tensor-core accumulator truncates, so short chains
@@ -123,7 +143,14 @@ int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, 
   g.C = D; g.ldc = ldd; g.M = M; g.N = N; g.K = K; g.batch = 1; g.splitk = 1;
   g.alpha = 1.f; g.beta = 0.f;
   g.epi = e.kind; g.E = e.E; g.lde = e.lde; g.dg = e.dg; g.da = e.da; g.damping = e.damping;
-  return launch_gemm(g, s);
+  const int rc = launch_gemm(g, s);
+  if (rc || npeer == 0) return rc;
+  float* pp[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int q = 0; q < npeer; ++q) pp[q] = peers[q];
+  const int64_t total = (int64_t)M * ldd;
+  peer_scatter_kernel<<<grid_for(total), 256, 0, s>>>(D, total, pp[0], pp[1], pp[2], pp[3], pp[4], pp[5], pp[6], npeer);
+  KFAC_LAUNCH_CHECK();
+  return KFAC_OK;
 }
 
 int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
@@ -187,6 +214,7 @@ extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int 
   for (int i = 0; i < count; ++i) {
     const kfac_precond_item& it = items[i];
     KFAC_CHECK_ARG(it.wgrad && it.P && it.g > 0 && it.a > 0 && it.ldp >= it.a, "precond item");
+    KFAC_CHECK_ARG(it.n_peers >= 0 && it.n_peers <= 7 && (it.n_peers == 0 || it.peer_P), "precond peers");
     const int g = it.g, a = it.a, lga = ld4(a), lag = ld4(g);
     gather_grad_kernel<<<grid_for((int64_t)g * lga), 256, 0, s>>>(it.wgrad, it.bgrad, it.grad_dtype, g, a, GR, lga);
     KFAC_LAUNCH_CHECK();
@@ -207,7 +235,7 @@ extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int 
       // (3) U^T[c, g'] = sum_k Qa[c, k] V2[g', k]                         (a x g)
       if ((rc = gemm_tn(it.qa, it.ldqa, T2, lga, T1, lag, a, g, a, Epi{}, s))) return rc;
       // (4) P[r, c] = sum_k Qg[r, k] U^T[c, k]                            (g x a)
-      if ((rc = gemm_tn(it.qg, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s))) return rc;
+      if ((rc = gemm_tn(it.qg, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers))) return rc;
     } else {
       if (!(it.a_inv && it.g_inv)) {
         set_error("precondition: A and G have not been inverted");
@@ -216,7 +244,7 @@ extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int 
       KFAC_CHECK_ARG(it.ldqa >= a && it.ldqg >= g, "inverse leading dims");
       // the damped inverses are symmetric: T^T = Ainv grad^T, P = Ginv T
       if ((rc = gemm_tn(it.a_inv, it.ldqa, GR, lga, T1, lag, a, g, a, Epi{}, s))) return rc;
-      if ((rc = gemm_tn(it.g_inv, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s))) return rc;
+      if ((rc = gemm_tn(it.g_inv, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers))) return rc;
     }
   }
   return KFAC_OK;
@@ -251,5 +279,37 @@ extern "C" int kfac_grad_update(const kfac_grad_item* items, int count, const fl
   }
   count_launch(count - 1);
   KFAC_LAUNCH_CHECK();
+  return KFAC_OK;
+}
+
+// ------------------------------------------------------------ peer memory (CUDA IPC)
+extern "C" int kfac_peer_alloc(size_t bytes, void** dev_ptr, void* handle64) {
+  KFAC_CHECK_ARG(bytes > 0 && dev_ptr && handle64, "peer_alloc args");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  void* p = nullptr;
+  KFAC_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return KFAC_ERR_CUDA; }
+  KFAC_CUDA(cudaMemset(p, 0, bytes));
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return KFAC_OK;
+}
+extern "C" int kfac_peer_open(const void* handle64, void** dev_ptr) {
+  KFAC_CHECK_ARG(handle64 && dev_ptr, "peer_open args");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  KFAC_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return KFAC_OK;
+}
+extern "C" int kfac_peer_close(void* dev_ptr) {
+  if (dev_ptr) KFAC_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return KFAC_OK;
+}
+extern "C" int kfac_peer_free(void* dev_ptr) {
+  if (dev_ptr) KFAC_CUDA(cudaFree(dev_ptr));
   return KFAC_OK;
 }

@@ -76,6 +76,15 @@ class ArenaCommunicator:
         self.calls['broadcast'] += 1
         dist.broadcast(flat, src=src, group=group)
 
+    def fence(self, token: torch.Tensor, group: Any = None) -> None:
+        """Group-wide ordering point after peer-to-peer stores: a one-element all-reduce (its
+        kernel starts after this rank's prior work on the stream and completes only when every
+        rank of the group has reached it)."""
+        if get_world_size(group) == 1:
+            return
+        self.calls['fence'] = self.calls.get('fence', 0) + 1
+        dist.all_reduce(token, group=group)
+
     # reference-compatible no-op (the arena design has no pending buckets)
     def flush_allreduce_buckets(self) -> None:
         return None
