@@ -84,6 +84,53 @@ def main():
                 print(f'world={world} method={method} symmetry_aware={sym} grad_worker_fraction={frac:.3f} '
                       f'collectives={pre._tdc.calls} worst rel-fro vs oracle = {t.item():.2e}', flush=True)
             ok = ok and t.item() < 1e-3
+    # wider layers (>= 64): the last precondition GEMM runs on the tcgen05 engine and its epilogue
+    # stores straight into the peers' arenas (fused compute + broadcast)
+    class Wide(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l1 = torch.nn.Linear(96, 160)
+            self.l2 = torch.nn.Linear(160, 128)
+            self.l3 = torch.nn.Linear(128, 5)
+
+        def forward(self, x):
+            return self.l3(torch.tanh(self.l2(torch.tanh(self.l1(x)))))
+
+    for frac in sorted({1.0 / world, 0.5 if world % 2 == 0 else 1.0 / world}):
+        torch.manual_seed(0)
+        ref_model = Wide()
+        model = copy.deepcopy(ref_model).to(dev)
+        torch.manual_seed(2)
+        gx = torch.randn(world * 16, 96)
+        gy = torch.randint(0, 5, (world * 16,))
+        x, y = gx[rank * 16:(rank + 1) * 16].to(dev), gy[rank * 16:(rank + 1) * 16].to(dev)
+        pre = KFACPreconditioner(model, damping=0.003, grad_worker_fraction=frac)
+        ref = OraclePreconditioner(ref_model, damping=0.003) if rank == 0 else None
+        worst = 0.0
+        for step in range(2):
+            model.zero_grad()
+            crit(model(x), y).backward()
+            for p in model.parameters():
+                dist.all_reduce(p.grad)
+                p.grad /= world
+            pre.step()
+            torch.cuda.synchronize()
+            if rank == 0:
+                ref_model.zero_grad()
+                (crit(ref_model(gx), gy) * world).backward()
+                for q in ref_model.parameters():
+                    q.grad /= world
+                ref.step()
+            for p, q in zip(model.parameters(), ref_model.parameters()):
+                want = q.grad.to(dev) if rank == 0 else torch.empty_like(p.grad)
+                dist.broadcast(want, src=0)
+                worst = max(worst, ((p.grad.double() - want.double()).norm() / want.double().norm()).item())
+        t = torch.tensor([worst], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f'world={world} wide-MLP grad_worker_fraction={frac:.3f} fused={pre._peer_p_bases is not None} '
+                  f'collectives={pre._tdc.calls} worst rel-fro vs oracle = {t.item():.2e}', flush=True)
+        ok = ok and t.item() < 1e-3
     dist.barrier()
     dist.destroy_process_group()
     if not ok:
