@@ -323,11 +323,37 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------ CPU arm
+def usable_cores():
+    """Host threads this process may really use: CPU affinity capped by the cgroup quota (a
+    container that sees 128 logical CPUs but owns a fraction of them would otherwise
+    oversubscribe MKL/OpenMP catastrophically) and by 32 (LAPACK eigh does not scale further)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        n = os.cpu_count() or 1
+    try:
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if q != 'max':
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            p = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:  # noqa: BLE001
+            pass
+    env = os.environ.get('KFAC_BENCH_CPU_THREADS')
+    if env:
+        return max(1, int(env))
+    return max(1, min(n, 32))
+
+
 def cpu_reference_loop(args, steps, warmup, budget):
     """The oracle port (same torch CPU ops as the reference) on the host cores."""
     from oracle.kfac_oracle import OraclePreconditioner
     make_model, shape, classes, hp, wl = make_workload(args.model, args.batch)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     model = make_model()
@@ -345,25 +371,51 @@ def cpu_reference_loop(args, steps, warmup, budget):
         t1 = time.perf_counter()
         opt.step()
         return t1 - t0
+    # every step is checked against the wall-clock budget; if not even the warm-up fits, the
+    # last completed step is the sample
     t_start = time.perf_counter()
-    for _ in range(warmup):
-        one()
-        if time.perf_counter() - t_start > budget / 3:
+    walls, kfacs = [], []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        k = one()
+        walls.append(time.perf_counter() - t0)
+        kfacs.append(k)
+        if time.perf_counter() - t_start + walls[-1] > budget:
             break
-    t0 = time.perf_counter()
-    done, step_s = 0, 0.0
-    for _ in range(steps):
-        step_s += one()
-        done += 1
-        per = (time.perf_counter() - t0) / done
-        if time.perf_counter() - t_start + per > budget:
-            break
-    total = time.perf_counter() - t0
+    if len(walls) > warmup:
+        walls, kfacs = walls[warmup:], kfacs[warmup:]
+    else:
+        walls, kfacs = walls[-1:], kfacs[-1:]
+    done, total, step_s = len(walls), sum(walls), sum(kfacs)
     return {'images_per_s': shape[0] * done / total, 'ms_per_step': total / done * 1e3,
             'kfac_step_ms': step_s / done * 1e3, 'steps_done': done, 'cores': cores, 'workload': wl}
 
 
 def cpu_baseline(args, steps, warmup, budget):
+    """Runs the CPU arm in a child process under a hard wall-clock limit so that the default
+    bench run always ends within minutes, whatever the host does."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--model', args.model,
+           '--steps', str(steps), '--warmup', str(warmup), '--budget-s', str(budget)]
+    if args.batch:
+        cmd += ['--batch', str(args.batch)]
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'OMP_NUM_THREADS'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=budget + 90, env=env)
+        line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
+        d = json.loads(line)
+        cb = d['cpu_baseline']
+        cb['kfac_step_ms'] = d.get('kfac_step_ms')
+        cb['ms_per_step'] = d.get('ms_per_step')
+        return cb
+    except Exception as e:  # noqa: BLE001
+        return {'value': None, 'unit': 'images/s', 'cores': usable_cores(), 'kind': 'port',
+                'sample': f'CPU oracle did not finish one step within {budget + 90:.0f} s ({type(e).__name__})'}
+
+
+def _cpu_baseline_inline(args, steps, warmup, budget):
     r = cpu_reference_loop(args, steps, warmup, budget)
     return {'value': r['images_per_s'], 'unit': 'images/s', 'cores': r['cores'], 'kind': 'port',
             'sample': f"{r['steps_done']} full step(s) of the same workload, no warm-up "
