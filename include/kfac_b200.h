@@ -114,7 +114,7 @@ typedef struct kfac_eigh_item {
                        ld = ldq -- typically the QT of the previous call (may alias QT); NULL = identity */
 } kfac_eigh_item;
 size_t kfac_eigh_workspace_bytes(const int* n, int count);
-/* max_sweeps <= 0 -> default (40); tol <= 0 -> automatic (pairs above 3e-6 are rotated; done when a sweep starts below 1e-5) */
+/* max_sweeps <= 0 -> default (40); tol <= 0 -> automatic (pairs above 3e-6 are rotated; done when a sweep starts below 2e-5 or its RMS contamination is below 3e-5) */
 int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* ws,
                       size_t ws_bytes, int max_sweeps, float tol, void* stream);
 

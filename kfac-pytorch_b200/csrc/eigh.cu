@@ -728,7 +728,7 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
   }
   if (max_sweeps <= 0) max_sweeps = 40;
   static const int env_inner = getenv("KFAC_EIGH_INNER") ? atoi(getenv("KFAC_EIGH_INNER")) : 0;
-  const int inner_sweeps = env_inner > 0 ? env_inner : 4;   // per block pair and round (early exit when nothing rotates)
+  const int inner_sweeps = env_inner > 0 ? env_inner : 2;   // per block pair and round (early exit when nothing rotates)
   char* base = (char*)ws;
   for (int i = 0; i < count; ++i) {
     EighMat& m = pl.mats[i];
@@ -740,8 +740,8 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     static const float env_conv = getenv("KFAC_EIGH_CONV_TOL") ? (float)atof(getenv("KFAC_EIGH_CONV_TOL")) : 0.f;
     static const float env_rms = getenv("KFAC_EIGH_RMS_TOL") ? (float)atof(getenv("KFAC_EIGH_RMS_TOL")) : 0.f;
     m.tol = tol > 0.f ? tol : (env_tol > 0.f ? env_tol : 3e-6f);   // pairs above this are re-diagonalised (see rel_off); ~ fp32 Gram noise floor
-    m.conv_tol = fmaxf(m.tol, tol > 0.f ? tol : (env_conv > 0.f ? env_conv : 1e-5f));
-    m.rms_tol = tol > 0.f ? tol : (env_rms > 0.f ? env_rms : 2e-5f);
+    m.conv_tol = fmaxf(m.tol, tol > 0.f ? tol : (env_conv > 0.f ? env_conv : 2e-5f));
+    m.rms_tol = tol > 0.f ? tol : (env_rms > 0.f ? env_rms : 3e-5f);
     m.nw_ratio = (3e-6f / sqrtf((float)m.n)) / m.tol;
     if (m.mode >= 2) {
       m.G = (float*)(base + (size_t)m.G); m.V = (float*)(base + (size_t)m.V);
