@@ -34,6 +34,10 @@ warnings.filterwarnings('ignore', message='Full backward hook is firing')
 METRIC = 'images/sec ResNet-50 K-FAC training step (fwd+bwd+factor hooks+preconditioner.step()+SGD), factor=inv=1'
 
 
+def metric_name(model):
+    return METRIC if model == 'resnet50' else METRIC.replace('ResNet-50', 'ResNet-32')
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -284,7 +288,7 @@ def run_b200(args):
     gemm_tf, gemm_ms = tc_gemm_microbench(lib, dev) if rank == 0 else (0.0, 0.0)
     burst_peak = float(peaks.get('bf16_tflops', 1590.0))
     out = {
-        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K,
+        'metric': metric_name(args.model), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / K, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (model fwd/bwd fp32; K-FAC path fp32)',
         'data': 'synthetic',
@@ -295,23 +299,27 @@ def run_b200(args):
                 'h2d_bytes_per_step': host_x.numel() * 4 + host_y.numel() * 8, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'kfac_phase_ms_per_step': {k: v / K for k, v in sorted(phase_ms.items())},
-        # dominant KERNEL: the tcgen05 pipeline (Gram/apply of the eigensolver, precondition and
-        # SYRK GEMMs are instances of it), timed alone on a 4096^3 problem
-        'roofline': {'kernel': 'tc::pipeline_kernel<GemmPolicy> (tcgen05 3xTF32 GEMM engine), 4096^3, isolated',
-                     'bound': 'tensor', 'achieved': gemm_tf, 'peak': burst_peak, 'unit': 'TFLOP/s',
-                     'frac': gemm_tf / burst_peak if burst_peak else None, 'traffic': None,
-                     'ms_per_launch': gemm_ms,
-                     'convention': 'algorithmic fp32 flops 2*M*N*K per launch / CUDA-event time; every product is '
-                                   'issued as 3 TF32 MMAs, so the tensor pipe executes 3x these flops at the TF32 '
-                                   'rate (= half the bf16 rate the peak was measured with)',
-                     'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if peaks else 'fallback 1590'},
-        # dominant PHASE of the step: the batched eigensolver
-        'roofline_phase': {'phase': 'kfac_eigh_batched (block one-sided Jacobi: Gram / smem Jacobi / apply rounds)',
-                           'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s',
-                           'frac': achieved / tensor_peak if tensor_peak else None,
-                           'convention': '9 n^3 flop per eigendecomposition (SURVEY.md 8d), rank-0 share, '
-                                         'duration = CUDA-event time of the inverse phase per step',
-                           'peak_source': peak_src},
+        # dominant launch of the step: ONE kfac_eigh_batched call (all factors this rank owns), timed
+        # live in the timed region with CUDA events on the launching stream
+        'roofline': {'kernel': 'kfac_eigh_batched (block one-sided Jacobi rounds: tcgen05 Gram -> smem Jacobi '
+                               '-> tcgen05 apply), one call per step over all factors of this rank',
+                     'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s',
+                     'frac': achieved / tensor_peak if tensor_peak else None, 'traffic': None,
+                     'ms_per_launch': inv_ms,
+                     'convention': 'algorithmic 9 n^3 flop per eigendecomposition (SURVEY.md 8d) summed over the '
+                                   "rank's factors / CUDA-event time of the call; the Jacobi rounds execute ~12 n^3 "
+                                   'flop per sweep as 3xTF32 MMAs and are latency/HBM bound (profiles/r01_ncu_full_pipeline.md: '
+                                   'Gram launch 88.9 MB DRAM traffic, tensor pipe 53 % active)',
+                     'peak_source': peak_src},
+        # the GEMM engine all tensor-core kernels instantiate, timed alone on a 4096^3 problem
+        'roofline_engine': {'kernel': 'tc::pipeline_kernel<GemmPolicy> (tcgen05 3xTF32 GEMM engine), 4096^3, isolated',
+                            'bound': 'tensor', 'achieved': gemm_tf, 'peak': burst_peak, 'unit': 'TFLOP/s',
+                            'frac': gemm_tf / burst_peak if burst_peak else None, 'traffic': None,
+                            'ms_per_launch': gemm_ms,
+                            'convention': 'algorithmic fp32 flops 2*M*N*K per launch / CUDA-event time; every product is '
+                                          'issued as 3 TF32 MMAs, so the tensor pipe executes 3x these flops at the TF32 '
+                                          'rate (= half the bf16 rate the peak was measured with)',
+                            'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if peaks else 'fallback 1590'},
         'algorithmic_flops_per_step': {'eigh_9n3': eig_flops, 'precondition_4ga(g+a)': prec_flops},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -388,7 +396,7 @@ def cpu_reference_loop(args, steps, warmup, budget):
         walls, kfacs = walls[-1:], kfacs[-1:]
     done, total, step_s = len(walls), sum(walls), sum(kfacs)
     return {'images_per_s': shape[0] * done / total, 'ms_per_step': total / done * 1e3,
-            'kfac_step_ms': step_s / done * 1e3, 'steps_done': done, 'cores': cores, 'workload': wl}
+            'kfac_step_ms': step_s / done * 1e3, 'steps_done': done, 'cores': cores, 'workload': wl, 'batch': int(shape[0])}
 
 
 def cpu_baseline(args, steps, warmup, budget):
@@ -429,11 +437,11 @@ def run_reference(args):
         return
     r = cpu_reference_loop(args, args.steps, min(args.warmup, 1), args.budget_s)
     out = {
-        'impl': 'reference', 'metric': METRIC, 'value': r['images_per_s'], 'unit': 'images/s',
+        'impl': 'reference', 'metric': metric_name(args.model), 'value': r['images_per_s'], 'unit': 'images/s',
         'n_gpus': args.gpus, 'steps': r['steps_done'], 'warmup': min(args.warmup, 1),
         'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': r['workload'], 'global_batch': None, 'parallelism': 'cpu, world_size 1'},
+        'config': {'workload': r['workload'], 'global_batch': r['batch'], 'parallelism': 'cpu, world_size 1'},
         'cpu_baseline': {'value': r['images_per_s'], 'unit': 'images/s', 'cores': r['cores'], 'kind': 'port',
                          'sample': f"{r['steps_done']} of {args.steps} requested steps within a "
                                    f"{args.budget_s:.0f} s budget; kfac step() {r['kfac_step_ms']:.0f} ms"},
