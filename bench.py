@@ -299,6 +299,10 @@ def run_b200(args):
                 'h2d_bytes_per_step': host_x.numel() * 4 + host_y.numel() * 8, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'kfac_phase_ms_per_step': {k: v / K for k, v in sorted(phase_ms.items())},
+        # preconditioner.step() itself (BASELINE.json: "K-FAC step() ms"): the phases step() runs, without the
+        # factor hooks that run inside forward/backward
+        'kfac_step_ms': sum(v for k, v in phase_ms.items() if k not in ('factor_a', 'factor_g')) / K,
+        'kfac_hooks_ms': sum(v for k, v in phase_ms.items() if k in ('factor_a', 'factor_g')) / K,
         # dominant launch of the step: ONE kfac_eigh_batched call (all factors this rank owns), timed
         # live in the timed region with CUDA events on the launching stream
         'roofline': {'kernel': 'kfac_eigh_batched (block one-sided Jacobi rounds: tcgen05 Gram -> smem Jacobi '
