@@ -39,6 +39,14 @@ static bool gram_mn_major() {
   return v != 0;
 } // block matrices at least this large use the tcgen05 Gram/apply kernels
 
+// Tensor-core class with 64-column blocks (128-wide pairs): half the rounds per sweep, one pair per
+// 128-row Gram tile (no discarded quadrants), 128x128 pair problems in the shared-memory Jacobi.
+static bool eigh_wide() {
+  static int v = -1;
+  if (v < 0) v = getenv("KFAC_EIGH_WIDE") ? atoi(getenv("KFAC_EIGH_WIDE")) : 0;
+  return v != 0;
+}
+
 struct alignas(64) EighMat {
   CUtensorMap tmG, tmGt, tmV, tmW;   // mode 3 only (TMA views of G, G^T, V and the W^T pair buffers)
   const float* F; float* Q; float* QT; float* d;
@@ -63,6 +71,7 @@ struct alignas(64) EighMat {
   float off_hist[12];          // diagnostics: convergence measure after each of the first sweeps
   int done;
   int sweeps;
+  int wide;                    // mode 3: block width 64 (pair width 128) instead of 32 (64)
 };
 
 // round-robin tournament: pair k of round r among nb (even) players
@@ -213,7 +222,7 @@ template <int N>
 __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const int* list,
                                                            int mode_block, int max_inner,
                                                            int tc_first = 0, int* active_list = nullptr,
-                                                           int* active_count = nullptr) {
+                                                           int* active_count = nullptr, int pair_shift = 0) {
   extern __shared__ float sm[];
   float (*M)[N + 1] = reinterpret_cast<float (*)[N + 1]>(sm);
   float (*W)[N + 1] = reinterpret_cast<float (*)[N + 1]>(sm + N * (N + 1));
@@ -227,8 +236,8 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
   float* Mg = nullptr;
   if (mode_block) {
     if (mt.done) return;
-    local = blockIdx.x - mt.inner_base;
-    Mg = mt.M + (int64_t)local * JP * JP;
+    local = blockIdx.x + pair_shift - mt.inner_base;
+    Mg = mt.M + (int64_t)local * N * N;
     for (int idx = tid; idx < N * N; idx += T) {
       const int i = idx / N, j = idx % N;
       M[i][j] = Mg[idx];
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
   }
 
   if (mode_block) {
-    float* Wg = mt.W + (int64_t)local * JP * JP;
+    float* Wg = mt.W + (int64_t)local * N * N;
     if (mt.mode == 3) { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx % N][idx / N]; }   // W^T
     else { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx / N][idx % N]; }
   } else {
@@ -570,6 +579,90 @@ struct ApplyPolicy {
   }
 };
 
+// ---- 128-wide pairs (EighMat::wide): one pair per Gram tile, apply with N = 128 ----
+struct GramWidePolicy {
+  using Params = GramParams;
+  struct Item { EighMat* mt; int local, I, J, kb0, kb1; };
+  static constexpr int BN = 128;
+  static constexpr bool B_IS_A = true;
+  static constexpr bool MN_MAJOR = false;
+  static constexpr int CHUNK = 1;
+  __device__ static void reset(Item&) {}
+  __device__ static int total_work(const Params&, int t) { return t; }
+  static constexpr uint32_t TX_BYTES = tc::PTILE;
+  __device__ static bool decode(const Params& p, int w, Item& it) {
+    const int gi = w / p.ksplits, sp = w % p.ksplits;
+    EighMat* mt = &p.mats[p.item_mat[gi]];
+    if (mt->done) return false;
+    it.mt = mt;
+    it.local = gi - mt->gram_base;
+    tournament(p.round % (mt->nb - 1), it.local, mt->nb, it.I, it.J);
+    const int kb_total = (mt->n + 31) / 32;
+    const int per = (kb_total + p.ksplits - 1) / p.ksplits;
+    it.kb0 = sp * per; it.kb1 = min(kb_total, it.kb0 + per);
+    return it.kb1 > it.kb0;
+  }
+  __device__ static int num_kb(const Params&, const Item& it) { return it.kb1 - it.kb0; }
+  __device__ static void load(const Params&, const Item& it, int kbi, uint8_t* a, uint8_t*, uint64_t* bar) {
+    const int kc = (it.kb0 + kbi) * 32;   // boxes {32 reduction indices, 64 rows of G^T}
+    tc::tma_load_3d(a, &it.mt->tmGt, bar, kc, it.I * 64, 0);
+    tc::tma_load_3d(a + 8192, &it.mt->tmGt, bar, kc, it.J * 64, 0);
+  }
+  __device__ static void store(const Params&, const Item& it, int row, int col0, float (&v)[32]) {
+    float* M = it.mt->M + (int64_t)it.local * 128 * 128 + row * 128 + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) atomicAdd(M + j, v[j]);
+  }
+};
+
+struct ApplyWidePolicy {
+  using Params = ApplyParams;
+  struct Item { EighMat* mt; int local, I, J, m0, which; int pr, active, n, np; float* G; float* V; float* Gt; };
+  static constexpr int BN = 128;
+  static constexpr bool B_IS_A = false;
+  static constexpr bool MN_MAJOR = false;
+  static constexpr int CHUNK = 8;
+  static constexpr uint32_t TX_BYTES = 2 * tc::PTILE;
+  __device__ static void reset(Item& it) { it.pr = -1; it.active = 0; }
+  __device__ static int total_work(const Params& p, int) { return *p.active_count * p.max_tiles * 2; }
+  __device__ static bool decode(const Params& p, int w, Item& it) {
+    it.which = w & 1;
+    const int t = (w >> 1) % p.max_tiles, slot = (w >> 1) / p.max_tiles;
+    if (slot != it.pr) {
+      it.pr = slot;
+      const int pr = p.active_list[slot];
+      EighMat* mt = &p.mats[p.pair_mat[pr]];
+      it.mt = mt;
+      it.local = pr - mt->pair_base;
+      it.active = 1;
+      it.n = mt->n; it.np = mt->np; it.G = mt->G; it.V = mt->V; it.Gt = mt->Gt;
+      tournament(p.round % (mt->nb - 1), it.local, mt->nb, it.I, it.J);
+    }
+    if (!it.active) return false;
+    it.m0 = t * 128;
+    return it.m0 < it.n;
+  }
+  __device__ static int num_kb(const Params&, const Item&) { return 4; }
+  __device__ static void load(const Params&, const Item& it, int kbi, uint8_t* a, uint8_t* b, uint64_t* bar) {
+    const int col = (kbi < 2 ? it.I : it.J) * 64 + (kbi & 1) * 32;
+    tc::tma_load_3d(a, it.which ? &it.mt->tmV : &it.mt->tmG, bar, col, it.m0, 0);
+    tc::tma_load_3d(b, &it.mt->tmW, bar, kbi * 32, 0, it.local);
+  }
+  __device__ static void store(const Params&, const Item& it, int row, int col0, float (&v)[32]) {
+    const int r = it.m0 + row;
+    if (r >= it.n) return;
+    const int np = it.np, cb = (col0 < 64 ? it.I : it.J) * 64 + (col0 & 32);
+    float* X = (it.which ? it.V : it.G) + (int64_t)r * np + cb;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(X + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    if (!it.which && it.Gt) {
+      float* T = it.Gt + (int64_t)cb * np + r;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) T[(int64_t)j * np] = v[j];
+    }
+  }
+};
+
 int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
                   int K, cudaStream_t s);
 int make_tmap_3d(CUtensorMap* tm, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
@@ -610,14 +703,16 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
       pl.simt_list.push_back(i);
     } else {
       m.mode = 3;
+      m.wide = eigh_wide() ? 1 : 0;
       m.np = (n[i] + 127) / 128 * 128;      // 128-row MMA tiles; nb % 4 == 0 -> pairs come in twos
-      m.nb = m.np / JB;
+      m.nb = m.np / (m.wide ? 64 : JB);
       m.pair_base = pl.tc_pairs;
       m.gram_base = pl.tc_gram_items;
+      const int gitems = m.wide ? m.nb / 2 : m.nb / 4;   // wide: one pair per Gram tile
       for (int k = 0; k < m.nb / 2; ++k) pl.tc_pair_mat.push_back(i);
-      for (int k = 0; k < m.nb / 4; ++k) pl.tc_gram_mat.push_back(i);
+      for (int k = 0; k < gitems; ++k) pl.tc_gram_mat.push_back(i);
       pl.tc_pairs += m.nb / 2;
-      pl.tc_gram_items += m.nb / 4;
+      pl.tc_gram_items += gitems;
       pl.max_nb = std::max(pl.max_nb, m.nb);
       pl.max_rows = std::max(pl.max_rows, n[i]);
       pl.tc_max_rows = std::max(pl.tc_max_rows, n[i]);
@@ -648,7 +743,8 @@ static void build_plan(const int* n, int count, EighPlan& pl) {
     EighMat& m = pl.mats[i];
     if (m.mode < 2) continue;
     const size_t sq = (size_t)m.np * m.np * sizeof(float);
-    const size_t pb = (size_t)(m.nb / 2) * JP * JP * sizeof(float);
+    const size_t pw = m.wide ? 128 : JP;
+    const size_t pb = (size_t)(m.nb / 2) * pw * pw * sizeof(float);
     m.G = (float*)take(sq); m.V = (float*)take(sq);      // offsets, rebased later
     if (m.mode == 3 && !gram_mn_major()) m.Gt = (float*)take(sq);
     m.M = (float*)take(pb); m.W = (float*)take(pb);
@@ -671,6 +767,8 @@ static int eigh_set_attrs() {   // once, from the calling thread, before any wor
   KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicyT<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
   KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicyT<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
   KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<ApplyPolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
+  KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramWidePolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
+  KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<ApplyWidePolicy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
   (void)tc_num_sms();
   done = true;
   return KFAC_OK;
@@ -752,14 +850,15 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
         // G / V: 128-row x 32-column boxes; G^T: 32-row boxes; W^T pair buffers as {k, j, pair}
         if ((rc = make_tmap_3d(&m.tmG, m.G, np, np, 1, rowb, rowb * np, 128))) return rc;
         if ((rc = make_tmap_3d(&m.tmV, m.V, np, np, 1, rowb, rowb * np, 128))) return rc;
-        if ((rc = make_tmap_3d(&m.tmGt, gram_mn_major() ? m.G : m.Gt, np, np, 1, rowb, rowb * np, 32))) return rc;
+        if ((rc = make_tmap_3d(&m.tmGt, gram_mn_major() ? m.G : m.Gt, np, np, 1, rowb, rowb * np, m.wide ? 64 : 32))) return rc;
       }
       m.M = (float*)(base + (size_t)m.M); m.W = (float*)(base + (size_t)m.W);
       m.pair_skip = (int*)(base + (size_t)m.pair_skip);
-      KFAC_CUDA(cudaMemsetAsync(m.M, 0, (size_t)(m.nb / 2) * JP * JP * sizeof(float), s));
+      const uint64_t pw = m.wide ? 128 : JP;   // pair width
+      KFAC_CUDA(cudaMemsetAsync(m.M, 0, (size_t)(m.nb / 2) * pw * pw * sizeof(float), s));
       if (m.mode == 3) {
         int rc;
-        if ((rc = make_tmap_3d(&m.tmW, m.W, JP, JP, m.nb / 2, JP * 4, JP * JP * 4, 64))) return rc;
+        if ((rc = make_tmap_3d(&m.tmW, m.W, pw, pw, m.nb / 2, pw * 4, pw * pw * 4, (uint32_t)pw))) return rc;
       }
     }
   }
@@ -835,6 +934,7 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
       if (m.Gt && (rc = gemm_tn_plain(m.V0T, m.ldq, m.F, m.n, m.Gt, m.np, m.n, m.n, m.n, s))) return rc;
     }
     const int rps = pl.max_nb - 1;                 // rounds per sweep of the largest matrix
+    const bool wide = pl.tc_pairs > 0 && eigh_wide();
     const int chunks = ceil_div(std::max(1, pl.simt_max_rows), GR);
     // tcgen05 class launch geometry
     const int sms = tc_num_sms();
@@ -873,21 +973,36 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
         }
         if (pl.tc_pairs > 0) {
           gp.round = r; ap.round = r;
-          if (gram_mn_major())
+          if (wide)
+            tc::pipeline_kernel<GramWidePolicy><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
+          else if (gram_mn_major())
             tc::pipeline_kernel<GramPolicyT<true>><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
           else
             tc::pipeline_kernel<GramPolicyT<false>><<<std::min(gram_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(gp, gram_total);
           count_launch(1);
         }
-        jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps,
-                                                                                 pl.total_pairs, d_active_list, d_active_count);
-        count_launch(1);
+        if (!wide) {
+          jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps,
+                                                                                   pl.total_pairs, d_active_list, d_active_count);
+          count_launch(1);
+        } else {   // 64x64 problems of the SIMT class, 128x128 problems of the tensor-core class
+          if (pl.total_pairs > 0) {
+            jacobi_smem_kernel<64><<<pl.total_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps);
+            count_launch(1);
+          }
+          jacobi_smem_kernel<128><<<pl.tc_pairs, 1024, SMEM128, s>>>(d_mats, d_all_pair + pl.total_pairs, 1, inner_sweeps, 0,
+                                                                     d_active_list, d_active_count, pl.total_pairs);
+          count_launch(1);
+        }
         if (pl.total_pairs > 0) {
           eigh_apply_kernel<<<dim3(pl.total_pairs, chunks, 2), 256, 0, s>>>(d_mats, d_pair_mat, r);
           count_launch(1);
         }
         if (pl.tc_pairs > 0) {
-          tc::pipeline_kernel<ApplyPolicy><<<std::min(apply_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(ap, apply_total);
+          if (wide)
+            tc::pipeline_kernel<ApplyWidePolicy><<<std::min(apply_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(ap, apply_total);
+          else
+            tc::pipeline_kernel<ApplyPolicy><<<std::min(apply_total, sms), tc::PTHREADS, tc::PSMEM, s>>>(ap, apply_total);
           count_launch(1);
         }
         eigh_ctl_kernel<<<1, 128, 0, s>>>(d_mats, d_block, nblock, r, d_flag, d_active_count);

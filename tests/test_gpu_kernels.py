@@ -240,6 +240,21 @@ def test_eigh_large(lib, dev):
         check_eigh(F, Q, d)
 
 
+def test_eigh_wide_pairs_variant():
+    # KFAC_EIGH_WIDE=1 (64-column blocks, 128x128 pair problems) is read once per process:
+    # run the tensor-core-class eigensolver tests again in a child with the switch on
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, KFAC_EIGH_WIDE='1')
+    here = os.path.abspath(__file__)
+    out = subprocess.run([sys.executable, '-m', 'pytest', here, '-q', '-m', 'gpu', '-x', '-k',
+                          'eigh_tc_class or eigh_large', '-p', 'no:cacheprovider'],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert '2 passed' in out.stdout, out.stdout[-500:]
+
+
 def test_dgda_and_inverse(lib, dev):
     from oracle import kfac_oracle as O
     torch.manual_seed(3)
