@@ -21,7 +21,8 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle.ref_import import import_reference  # noqa: E402
-from oracle.models import SmallConvNet, TinyModel  # noqa: E402
+from oracle.fixture_util import loss_by_name, materialize_kwargs  # noqa: E402
+from oracle.models import MODEL_ZOO, GeomConvNet, SeqModel, SmallConvNet, TinyModel  # noqa: E402
 
 kfac = import_reference()
 from kfac.assignment import KAISAAssignment  # noqa: E402
@@ -75,10 +76,15 @@ def fixture(name, make_model, batches, loss_fn, steps, micro=1, **kw):
     torch.manual_seed(0)
     model = make_model()
     init = {k: v.clone() for k, v in model.state_dict().items()}
-    rec = run_reference(model, batches, loss_fn, steps, micro=micro, **kw)
+    loss_name = loss_fn if isinstance(loss_fn, str) else None
+    if loss_name:
+        loss_fn = loss_by_name(loss_name)
+    rec = run_reference(model, batches, loss_fn, steps, micro=micro, **materialize_kwargs(kw))
     kw_ser = {k: (v if not hasattr(v, 'name') else v.name) for k, v in kw.items()}
+    assert make_model.__name__ in MODEL_ZOO
     torch.save({'init': init, 'batches': batches, 'steps': steps, 'micro': micro,
-                'kwargs': kw_ser, 'record': rec}, os.path.join(GOLD, name + '.pt'))
+                'kwargs': kw_ser, 'record': rec, 'model': make_model.__name__,
+                'loss': loss_name}, os.path.join(GOLD, name + '.pt'))
     print('wrote', name, os.path.getsize(os.path.join(GOLD, name + '.pt')) // 1024, 'KiB')
 
 
@@ -107,6 +113,25 @@ def main():
             compute_method='inverse', damping=0.003)
     fixture('conv_accum', SmallConvNet, conv_batches, ce, steps=3, micro=2,
             accumulation_steps=2, damping=0.003)
+
+    # ---- widened cases (round 1): per-axis conv geometry, (batch, seq, feature) Linear inputs,
+    # callable hyper-parameters, skip_layers
+    torch.manual_seed(3)
+    geom_batches = [(torch.randn(2, 2, 11, 9), torch.randint(0, 4, (2,))) for _ in range(2)]
+    fixture('geom_eigen', GeomConvNet, geom_batches, 'ce', steps=3, damping=0.003)
+    fixture('geom_inverse', GeomConvNet, geom_batches, 'ce', steps=2, damping=0.003,
+            compute_method='inverse')
+    torch.manual_seed(4)
+    seq_batches = [(torch.randn(2, 5, 12), torch.randn(2, 5, 7)) for _ in range(2)]
+    fixture('seq_eigen', SeqModel, seq_batches, 'mse_sum', steps=3, damping=0.002)
+    fixture('tiny_callable', TinyModel, tiny_batches, 'mse_sum', steps=6,
+            damping={'schedule': [0.004, 0.003, 0.002, 0.001]},
+            factor_decay={'schedule': [0.9, 0.95]},
+            kl_clip={'schedule': [0.002, 0.001, 0.0005]},
+            lr={'schedule': [0.2, 0.1, 0.05]},
+            inv_update_steps={'schedule': [1, 1, 2]})
+    fixture('conv_skip', SmallConvNet, conv_batches, 'ce', steps=3, damping=0.003,
+            skip_layers=['conv3', 'Linear'])
 
     # ---- KAISA placement (kfac/assignment.py:227-395)
     ident = lambda ranks: tuple(ranks)  # noqa: E731

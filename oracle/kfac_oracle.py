@@ -169,6 +169,16 @@ class OracleLayer:
         return conv2d_g_factor(g) if self.is_conv else linear_g_factor(g)
 
 
+def _hp(name):
+    def get(self):
+        v = getattr(self, '_' + name)
+        return v(self.steps) if callable(v) else v
+
+    def put(self, v):
+        setattr(self, '_' + name, v)
+    return property(get, put)
+
+
 class OraclePreconditioner:
     """Single-process restatement of BaseKFACPreconditioner.step()
     (kfac/base_preconditioner.py:310-382) + hooks (:437-479) on CPU.
@@ -178,18 +188,26 @@ class OraclePreconditioner:
     timed CPU baseline (`bench.py`, kind "port").
     """
 
+    factor_update_steps = _hp('factor_update_steps')
+    inv_update_steps = _hp('inv_update_steps')
+    damping = _hp('damping')
+    factor_decay = _hp('factor_decay')
+    kl_clip = _hp('kl_clip')
+    lr = _hp('lr')
+
     def __init__(self, model, *, factor_update_steps=1, inv_update_steps=1,
                  damping=0.001, factor_decay=0.95, kl_clip=0.001, lr=0.1,
                  accumulation_steps=1, compute_method='eigen',
                  prediv=True, skip_layers=None,
                  grad_scaler: Callable[[], float] | None = None):
         import re
-        self.factor_update_steps = factor_update_steps
-        self.inv_update_steps = inv_update_steps
-        self.damping = damping
-        self.factor_decay = factor_decay
-        self.kl_clip = kl_clip
-        self.lr = lr
+        # constants or callables of the step count (base_preconditioner.py:160-213)
+        self._factor_update_steps = factor_update_steps
+        self._inv_update_steps = inv_update_steps
+        self._damping = damping
+        self._factor_decay = factor_decay
+        self._kl_clip = kl_clip
+        self._lr = lr
         self.accumulation_steps = accumulation_steps
         self.compute_method = compute_method
         self.prediv = prediv

@@ -45,6 +45,42 @@ class SmallConvNet(nn.Module):
         return self.fc(x)
 
 
+class GeomConvNet(nn.Module):
+    """Asymmetric kernels / strides / paddings (modules.py:210-237 handles each axis on its
+    own): (3,2) stride (2,1) pad (1,0) with bias; 5x5 stride 2 pad 2; (1,3) pad (0,1); Linear
+    without bias."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(2, 4, (3, 2), stride=(2, 1), padding=(1, 0), bias=True)
+        self.conv2 = nn.Conv2d(4, 5, 5, stride=2, padding=2, bias=False)
+        self.conv3 = nn.Conv2d(5, 6, (1, 3), stride=1, padding=(0, 1), bias=True)
+        self.fc = nn.Linear(6, 4, bias=False)
+
+    def forward(self, x):
+        x = F.relu(self.conv1(x))
+        x = F.relu(self.conv2(x))
+        x = F.relu(self.conv3(x))
+        return self.fc(F.adaptive_avg_pool2d(x, 1).flatten(1))
+
+
+class SeqModel(nn.Module):
+    """Linear layers on (batch, seq, features) inputs: all leading dims are flattened into
+    rows (modules.py:129,140)."""
+
+    def __init__(self):
+        super().__init__()
+        self.proj = nn.Linear(12, 16)
+        self.out = nn.Linear(16, 7, bias=False)
+
+    def forward(self, x):
+        return self.out(torch.tanh(self.proj(x)))
+
+
+MODEL_ZOO = {'TinyModel': TinyModel, 'SmallConvNet': SmallConvNet, 'GeomConvNet': GeomConvNet,
+             'SeqModel': SeqModel}
+
+
 # ------------------------------------------------------------------ ResNets
 class _BasicBlock(nn.Module):
     def __init__(self, inp, out, stride):

@@ -29,12 +29,24 @@ def load_fixture(name):
 MODELS = {}
 
 
-def model_for(name):
-    from oracle.models import SmallConvNet, TinyModel
+GOLDEN_NAMES = ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
+                'conv_eigen', 'conv_inverse', 'conv_accum',
+                # widened cases: per-axis conv geometry, (batch, seq, feature) Linear inputs,
+                # callable hyper-parameters, skip_layers
+                'geom_eigen', 'geom_inverse', 'seq_eigen', 'tiny_callable', 'conv_skip']
+
+
+def model_for(name, fx=None):
+    from oracle.models import MODEL_ZOO, SmallConvNet, TinyModel
+    if fx is not None and fx.get('model'):
+        return MODEL_ZOO[fx['model']]()
     return TinyModel() if name.startswith('tiny') else SmallConvNet()
 
 
-def loss_for(name):
+def loss_for(name, fx=None):
+    if fx is not None and fx.get('loss'):
+        from oracle.fixture_util import loss_by_name
+        return loss_by_name(fx['loss'])
     if name.startswith('tiny'):
         return torch.nn.MSELoss(reduction='sum')
     return torch.nn.CrossEntropyLoss()
@@ -47,13 +59,14 @@ def replay(name, make_precond, device='cpu', get_layers=None):
     {layer_name: (A, G)} after each step.  Yields (step_idx, golden_step,
     model, pre) after every step().
     """
+    from oracle.fixture_util import materialize_kwargs
     fx = load_fixture(name)
-    model = model_for(name)
+    model = model_for(name, fx)
     model.load_state_dict(fx['init'])
     model.to(device)
-    pre = make_precond(model, **fx['kwargs'])
+    pre = make_precond(model, **materialize_kwargs(fx['kwargs']))
     opt = torch.optim.SGD(model.parameters(), lr=0.05)
-    loss_fn = loss_for(name)
+    loss_fn = loss_for(name, fx)
     bi = 0
     for s in range(fx['steps']):
         opt.zero_grad()
@@ -68,5 +81,4 @@ def replay(name, make_precond, device='cpu', get_layers=None):
 
 @pytest.fixture
 def golden_names():
-    return ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
-            'conv_eigen', 'conv_inverse', 'conv_accum']
+    return list(GOLDEN_NAMES)

@@ -7,7 +7,7 @@ import copy
 import pytest
 import torch
 
-from conftest import rel_fro, replay
+from conftest import GOLDEN_NAMES, rel_fro, replay
 
 pytestmark = pytest.mark.gpu
 
@@ -17,8 +17,7 @@ pytestmark = pytest.mark.gpu
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
-NAMES = ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
-         'conv_eigen', 'conv_inverse', 'conv_accum']
+NAMES = list(GOLDEN_NAMES)
 
 
 def _mk(model, **kw):

@@ -6,11 +6,10 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN, rel_fro, replay
+from conftest import GOLDEN, GOLDEN_NAMES, rel_fro, replay
 from oracle import kfac_oracle as O
 
-NAMES = ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched',
-         'conv_eigen', 'conv_inverse', 'conv_accum']
+NAMES = list(GOLDEN_NAMES)
 
 
 def test_get_cov_reference_vectors():
