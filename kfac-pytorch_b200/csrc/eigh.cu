@@ -218,7 +218,14 @@ __global__ void __launch_bounds__(256) eigh_gram_kernel(EighMat* mats, const int
 //                 the pair buffer, W written to the pair buffer.
 // mode_block = 0: blockIdx.x indexes `list`; the matrix itself is solved,
 //                 Q and d written directly.
-template <int N>
+// OPT (compile-time, experimental, selected by KFAC_EIGH_JOPT; 0 = the validated default):
+//   bit 0  rotation parameters from MUFU rsqrt/rcp + one Newton step instead of IEEE div/sqrt chains
+//   bit 1  block mode: the first inner sweep visits only the N/2 x N/2 cross pairs (the two diagonal
+//          blocks of a pair Gram are already diagonal from earlier rounds) -- N/2 steps instead of N-1
+//   bit 2  fewer shared-memory instructions per step (the kernel is bound by them: ~56 LDS/STS per
+//          thread and step): (c, s, p, q) of a rotation packed into one float4, and only the upper
+//          triangle of M is kept up to date (block pairs a <= b)
+template <int N, int OPT = 0>
 __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const int* list,
                                                            int mode_block, int max_inner,
                                                            int tc_first = 0, int* active_list = nullptr,
@@ -229,6 +236,8 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
   float* cs = sm + 2 * N * (N + 1);       // c[N/2], s[N/2]
   __shared__ float redmax[32];
   __shared__ int sh_big;
+  __shared__ int sh_within;
+  __shared__ float4 rot4[(OPT & 4) ? N / 2 : 1];
   constexpr int T = N * 8;   // 512 / 1024 threads: the 2x2-block update is latency bound, more threads = fewer serial LDS/STS
   const int tid = threadIdx.x;
   EighMat& mt = mats[list[blockIdx.x]];
@@ -262,14 +271,17 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
     const float max_diag = __uint_as_float(mt.max_diag);   // running maximum over all rounds
     const float nw_ratio = mt.nw_ratio;
     float mx = 0.f, ss = 0.f;
+    int within = 0;   // OPT bit 1: some pair INSIDE one of the two blocks is above tol
     for (int idx = tid; idx < N * N; idx += T) {
       const int i = idx / N, j = idx % N;
       if (j > i) {
         const float r = rel_off(M[i][j], M[i][i], M[j][j], max_diag, nw_ratio);
         mx = fmaxf(mx, r);
         ss = fmaf(fminf(r, 1.f), fminf(r, 1.f), ss);
+        if ((OPT & 2) && (i < N / 2) == (j < N / 2) && !(r < mt.tol)) within = 1;
       }
     }
+    if (OPT & 2) { within = __syncthreads_or(within); if (tid == 0) sh_within = within; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((tid & 31) == 0 && ss > 0.f) atomicAdd(&mt.sweep_sumsq, ss);
@@ -300,32 +312,95 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
   const float blk_nw_ratio = mode_block ? mt.nw_ratio : 0.f;
 
   int* pq = reinterpret_cast<int*>(cs + N);   // (p,q) of every pair of the current step
-  for (int sweep = 0; sweep < max_inner; ++sweep) {
+  if (OPT & 2) __syncthreads();
+  const bool bip_first = (OPT & 2) && mode_block && !sh_within;
+  for (int sweep = 0; sweep < max_inner + (bip_first ? 1 : 0); ++sweep) {
     int rotated_sweep = 0;
     if (tid == 0) sh_big = 0;   // set when some |sin| >= 2e-3 in this sweep
     __syncthreads();
-    for (int st = 0; st < N - 1; ++st) {
+    const bool bip = bip_first && sweep == 0;
+    for (int st = 0; st < (bip ? N / 2 : N - 1); ++st) {
       int rotated = 0;
       if (tid < N / 2) {
         int p, q;
-        tournament(st, tid, N, p, q);
+        if (bip) { p = tid; q = N / 2 + (tid + st) % (N / 2); }
+        else tournament(st, tid, N, p, q);
         const float apq = M[p][q], app = M[p][p], aqq = M[q][q];
         float c = 1.f, s = 0.f;
         const float thr = mode_block ? pair_den(app, aqq, blk_max_diag, blk_nw_ratio) : sqrtf(fabsf(app * aqq));
         if (fabsf(apq) > tol_in * thr) {
-          const float tau = (aqq - app) / (2.f * apq);
-          const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-          c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's bias makes column norms drift
-          s = t * c;
+          if (OPT & 1) {
+            // t = sign(a b) |b| / (|a| + sqrt(a^2 + b^2)), a = aqq - app, b = 2 apq; operands scaled
+            // by 1/max(|a|,|b|) so the squares cannot overflow; rsqrt + one Newton step is
+            // accurate to ~1 ulp without the bias of the raw MUFU value
+            float a = aqq - app, b = 2.f * apq;
+            const float sc = __frcp_rn(fmaxf(fabsf(a), fabsf(b)));
+            a *= sc; b *= sc;
+            const float x = fmaf(a, a, b * b);
+            float r = rsqrtf(x);
+            r = r * fmaf(-0.5f * x * r, r, 1.5f);
+            const float t = copysignf(fabsf(b), (a < 0.f) != (b < 0.f) ? -1.f : 1.f) * __frcp_rn(fabsf(a) + x * r);
+            const float y = fmaf(t, t, 1.f);
+            float rc = rsqrtf(y);
+            rc = rc * fmaf(-0.5f * y * rc, rc, 1.5f);
+            c = rc;
+            s = t * c;
+          } else {
+            const float tau = (aqq - app) / (2.f * apq);
+            const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+            c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's bias makes column norms drift
+            s = t * c;
+          }
           if (s != 0.f) { rotated = 1; if (fabsf(s) >= 2e-3f) sh_big = 1; }
         }
-        cs[tid] = c;
-        cs[N / 2 + tid] = s;
-        pq[tid] = p | (q << 16);
+        if (OPT & 4) rot4[tid] = make_float4(c, s, __int_as_float(p), __int_as_float(q));
+        else {
+          cs[tid] = c;
+          cs[N / 2 + tid] = s;
+          pq[tid] = p | (q << 16);
+        }
       }
       // barrier + "did anybody rotate": a step without rotations is skipped entirely
       if (!__syncthreads_or(rotated)) continue;
       rotated_sweep = 1;
+      if (OPT & 4) {
+        auto MS = [&](int i, int j) -> float& { return i <= j ? M[i][j] : M[j][i]; };
+        for (int idx = tid; idx < (N / 2) * (N / 2); idx += T) {
+          const int b = idx % (N / 2), a = idx / (N / 2);
+          if (a > b) continue;                       // the mirror block is never read
+          const float4 ra = rot4[a], rb = rot4[b];
+          const float ca = ra.x, sa = ra.y, cb = rb.x, sb = rb.y;
+          if (sa == 0.f && sb == 0.f) continue;
+          const int pa = __float_as_int(ra.z), qa = __float_as_int(ra.w);
+          const int pb = __float_as_int(rb.z), qb = __float_as_int(rb.w);
+          if (a == b) {                              // diagonal 2x2 block: symmetric, 3 entries
+            const float m00 = M[pa][pa], m01 = M[pa][qa], m11 = M[qa][qa];
+            const float n00 = ca * m00 - sa * m01, n01 = sa * m00 + ca * m01;
+            const float n10 = ca * m01 - sa * m11, n11 = sa * m01 + ca * m11;
+            M[pa][pa] = ca * n00 - sa * n10;
+            M[pa][qa] = ca * n01 - sa * n11;
+            M[qa][qa] = sa * n01 + ca * n11;
+          } else {
+            float &r00 = MS(pa, pb), &r01 = MS(pa, qb), &r10 = MS(qa, pb), &r11 = MS(qa, qb);
+            const float m00 = r00, m01 = r01, m10 = r10, m11 = r11;
+            const float n00 = cb * m00 - sb * m01, n01 = sb * m00 + cb * m01;
+            const float n10 = cb * m10 - sb * m11, n11 = sb * m10 + cb * m11;
+            r00 = ca * n00 - sa * n10;
+            r01 = ca * n01 - sa * n11;
+            r10 = sa * n00 + ca * n10;
+            r11 = sa * n01 + ca * n11;
+          }
+        }
+        for (int idx = tid; idx < N * (N / 2); idx += T) {
+          const int i = idx % N, k = idx / N;
+          const float4 r = rot4[k];
+          if (r.y == 0.f) continue;
+          const int p = __float_as_int(r.z), q = __float_as_int(r.w);
+          const float u = W[i][p], v = W[i][q];
+          W[i][p] = r.x * u - r.y * v;
+          W[i][q] = r.y * u + r.x * v;
+        }
+      } else {
       // M <- J^T M J on independent 2x2 blocks (pair a rows) x (pair b columns)
       for (int idx = tid; idx < (N / 2) * (N / 2); idx += T) {
         const int b = idx % (N / 2), a = idx / (N / 2);
@@ -349,6 +424,7 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
         const float u = W[i][p], v = W[i][q];
         W[i][p] = c * u - s * v;
         W[i][q] = s * u + c * v;
+      }
       }
       __syncthreads();
     }
@@ -982,8 +1058,23 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
           count_launch(1);
         }
         if (!wide) {
-          jacobi_smem_kernel<64><<<pl.total_pairs + pl.tc_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps,
-                                                                                   pl.total_pairs, d_active_list, d_active_count);
+          // experimental inner-solver variants (see jacobi_smem_kernel): KFAC_EIGH_JOPT = bit mask 1 | 2 | 4
+          static const int jopt = getenv("KFAC_EIGH_JOPT") ? (atoi(getenv("KFAC_EIGH_JOPT")) & 7) : 0;
+          const int nblk = pl.total_pairs + pl.tc_pairs;
+#define KFAC_JACOBI_BLOCK(OPT)                                                                              \
+  jacobi_smem_kernel<64, OPT><<<nblk, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps, pl.total_pairs, \
+                                                        d_active_list, d_active_count, 0)
+          switch (jopt) {
+            case 1: KFAC_JACOBI_BLOCK(1); break;
+            case 2: KFAC_JACOBI_BLOCK(2); break;
+            case 3: KFAC_JACOBI_BLOCK(3); break;
+            case 4: KFAC_JACOBI_BLOCK(4); break;
+            case 5: KFAC_JACOBI_BLOCK(5); break;
+            case 6: KFAC_JACOBI_BLOCK(6); break;
+            case 7: KFAC_JACOBI_BLOCK(7); break;
+            default: KFAC_JACOBI_BLOCK(0); break;
+          }
+#undef KFAC_JACOBI_BLOCK
           count_launch(1);
         } else {   // 64x64 problems of the SIMT class, 128x128 problems of the tensor-core class
           if (pl.total_pairs > 0) {
