@@ -1,0 +1,98 @@
+// EXPERIMENTAL: device side of jacobi_systolic.cuh (see there).  Not used by the product path;
+// exported only through kfac_experimental_jacobi_systolic() so that round 2 can validate and time
+// it against jacobi_smem_kernel before wiring it into the block solver of eigh.cu.
+#include "common.cuh"
+#include "jacobi_systolic.cuh"
+
+namespace kfac {
+
+// One CTA per matrix: TB bulk threads + N/2 crit threads.  F: count matrices n x n (n <= N),
+// Q: eigenvectors in columns (ld n), d: eigenvalues (unsorted, clamped at 0).
+template <int N, int TB>
+__global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_kernel(const float* F, int n, float* Q, float* d,
+                                                                    int max_sweeps) {
+  using namespace sysj;
+  constexpr int h = N / 2, LD = N;
+  extern __shared__ float sm[];
+  float* M = sm;
+  float* W = sm + N * N;
+  Rot* rot = reinterpret_cast<Rot*>(W + N * N);
+  int* flag = reinterpret_cast<int*>(rot + h);
+  float* colscale = reinterpret_cast<float*>(flag + 4);
+  const int tid = threadIdx.x, T = TB + h;
+  const bool is_crit = tid >= TB;
+  const int k = tid - TB;
+  const float* Fm = F + (size_t)blockIdx.x * n * n;
+  for (int idx = tid; idx < N * N; idx += T) {
+    const int i = idx / N, j = idx % N;
+    M[idx] = (i < n && j < n) ? Fm[(size_t)i * n + j] : 0.f;
+    W[idx] = (i == j) ? 1.f : 0.f;
+  }
+  if (tid == 0) *flag = 0;
+  __syncthreads();
+  const Criteria cr{0, 1e-7f, 0.f, 0.f};
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (is_crit) {
+      int f = 0;
+      rot[k] = first_rotation<N, LD>(k, cr, M, f);
+      if (f) atomicOr(flag, f);
+    }
+    __syncthreads();
+    for (int st = 0; st < N - 1; ++st) {
+      const bool more = st < N - 2;
+      BulkRegs<N, TB> regs;
+      CritRegs cregs;
+      if (!is_crit) bulk_load<N, LD, TB>(tid, rot, M, W, regs);
+      else if (more) crit_load<N, LD>(k, rot, M, cregs);
+      __syncthreads();
+      if (!is_crit) bulk_store<N, LD, TB>(tid, M, W, regs);
+      else if (more) {
+        int f = 0;
+        rot[k] = crit_rotation(cr, cregs, f);
+        if (f) atomicOr(flag, f);
+      }
+      __syncthreads();
+    }
+    const int f = *flag;
+    __syncthreads();
+    if (tid == 0) *flag = 0;
+    // all rotations of the sweep tiny (or none): the leftovers are second order
+    if (!(f & 1) || !(f & 2)) break;
+  }
+  __syncthreads();
+  // rescale by the (rounding-drifted) column norms of W
+  for (int j = tid; j < N; j += T) {
+    float ww = 0.f;
+    for (int i = 0; i < N; ++i) ww = fmaf(W[i * LD + j], W[i * LD + j], ww);
+    colscale[j] = ww > 0.f ? 1.f / sqrtf(ww) : 0.f;
+  }
+  __syncthreads();
+  float* Qm = Q + (size_t)blockIdx.x * n * n;
+  for (int idx = tid; idx < n * n; idx += T) {
+    const int i = idx / n, j = idx % n;
+    Qm[idx] = W[i * LD + j] * colscale[j];
+  }
+  for (int j = tid; j < n; j += T) d[(size_t)blockIdx.x * n + j] = fmaxf(M[j * LD + j] * colscale[j] * colscale[j], 0.f);
+}
+
+template <int N, int TB>
+static int launch_systolic(const float* F, int n, int count, float* Q, float* d, int max_sweeps, cudaStream_t s) {
+  const size_t smem = ((size_t)2 * N * N + N /*rot*/ + 4 /*flag*/ + N /*colscale*/) * sizeof(float);
+  KFAC_CUDA(cudaFuncSetAttribute(jacobi_systolic_kernel<N, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  jacobi_systolic_kernel<N, TB><<<count, TB + N / 2, smem, s>>>(F, n, Q, d, max_sweeps);
+  KFAC_LAUNCH_CHECK();
+  return KFAC_OK;
+}
+
+}  // namespace kfac
+
+// Not declared in include/kfac_b200.h on purpose (experimental, test-only).
+extern "C" int kfac_experimental_jacobi_systolic(const float* F, int n, int count, float* Q, float* d, int max_sweeps,
+                                                 void* stream) {
+  using namespace kfac;
+  KFAC_CHECK_ARG(F && Q && d && n > 0 && n <= 128 && count > 0, "jacobi_systolic arguments");
+  if (max_sweeps <= 0) max_sweeps = 24;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n <= 64) return launch_systolic<64, 512>(F, n, count, Q, d, max_sweeps, s);
+  return launch_systolic<128, 960>(F, n, count, Q, d, max_sweeps, s);
+}

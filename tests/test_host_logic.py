@@ -206,3 +206,18 @@ def test_arena_entries_are_16_byte_aligned():
                         assert off % 4 == 0, (method, shape)
                         off += _storage_numel(shape)
     assert _storage_numel((147,)) == 148 and _storage_numel((10, 21)) == 10 * 24
+
+
+def test_systolic_jacobi_host_emulation(tmp_path):
+    """The experimental data-moving Jacobi (csrc/jacobi_systolic.cuh) is plain inline code on explicit
+    worker indices: replay it on the CPU (schedule, crit-thread prediction, convergence)."""
+    import shutil
+    import subprocess
+    if shutil.which('g++') is None:
+        pytest.skip('no g++')
+    exe = tmp_path / 'jsh'
+    src = os.path.join(ROOT, 'tests', 'host', 'jacobi_systolic_host.cpp')
+    inc = os.path.join(ROOT, 'kfac-pytorch_b200', 'csrc')
+    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-std=c++17', '-I', inc, src, '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith('OK'), out.stdout[-2000:]
