@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_kernel(const float
   float* M = sm;
   float* W = sm + N * N;
   Rot* rot = reinterpret_cast<Rot*>(W + N * N);
-  int* flag = reinterpret_cast<int*>(rot + h);
+  int* flag = reinterpret_cast<int*>(rot + 2 * h);   // rot: 2 x h (double buffered)
   float* colscale = reinterpret_cast<float*>(flag + 4);
   const int tid = threadIdx.x, T = TB + h;
   const bool is_crit = tid >= TB;
@@ -28,34 +28,47 @@ __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_kernel(const float
     M[idx] = (i < n && j < n) ? Fm[(size_t)i * n + j] : 0.f;
     W[idx] = (i == j) ? 1.f : 0.f;
   }
-  if (tid == 0) *flag = 0;
+  if (tid == 0) { flag[0] = 0; flag[1] = 0; }
   __syncthreads();
   const Criteria cr{0, 1e-7f, 0.f, 0.f};
+  // rot is double buffered by step parity: the crit threads publish the rotations of step t+1
+  // while the bulk threads may still be reading those of step t
+  int par = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    int* fl = flag + (sweep & 1);              // "somebody rotated / rotated a lot" of this sweep
+    if (tid == 0) flag[(sweep + 1) & 1] = 0;   // the next sweep's word: last read one sweep ago
     if (is_crit) {
       int f = 0;
-      rot[k] = first_rotation<N, LD>(k, cr, M, f);
-      if (f) atomicOr(flag, f);
+      rot[par * h + k] = first_rotation<N, LD>(k, cr, M, f);
+      if (f) atomicOr(fl, f);
     }
     __syncthreads();
     for (int st = 0; st < N - 1; ++st) {
       const bool more = st < N - 2;
-      BulkRegs<N, TB> regs;
-      CritRegs cregs;
-      if (!is_crit) bulk_load<N, LD, TB>(tid, rot, M, W, regs);
-      else if (more) crit_load<N, LD>(k, rot, M, cregs);
-      __syncthreads();
-      if (!is_crit) bulk_store<N, LD, TB>(tid, M, W, regs);
-      else if (more) {
-        int f = 0;
-        rot[k] = crit_rotation(cr, cregs, f);
-        if (f) atomicOr(flag, f);
+      const Rot* rcur = rot + par * h;
+      if (!is_crit) {
+        BulkRegs<N, TB> regs;
+        bulk_load<N, LD, TB>(tid, rcur, M, W, regs);
+        // every load of the step (bulk and crit) is done before anybody stores in place
+        asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+        bulk_store<N, LD, TB>(tid, M, W, regs);
+      } else {
+        CritRegs cregs;
+        if (more) crit_load<N, LD>(k, rcur, M, cregs);
+        // arrive without waiting: the div/sqrt chain of the next rotation runs while the bulk
+        // threads finish loading and then store
+        asm volatile("bar.arrive 1, %0;" ::"r"(T) : "memory");
+        if (more) {
+          int f = 0;
+          rot[(par ^ 1) * h + k] = crit_rotation(cr, cregs, f);
+          if (f) atomicOr(fl, f);
+        }
       }
       __syncthreads();
+      par ^= 1;
     }
-    const int f = *flag;
-    __syncthreads();
-    if (tid == 0) *flag = 0;
+    const int f = *fl;   // complete: the last step ended with a barrier
+    __syncthreads();     // everybody has read it before thread 0 recycles the word (two sweeps later)
     // all rotations of the sweep tiny (or none): the leftovers are second order
     if (!(f & 1) || !(f & 2)) break;
   }
@@ -77,7 +90,7 @@ __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_kernel(const float
 
 template <int N, int TB>
 static int launch_systolic(const float* F, int n, int count, float* Q, float* d, int max_sweeps, cudaStream_t s) {
-  const size_t smem = ((size_t)2 * N * N + N /*rot*/ + 4 /*flag*/ + N /*colscale*/) * sizeof(float);
+  const size_t smem = ((size_t)2 * N * N + 2 * N /*rot x2*/ + 4 /*flag*/ + N /*colscale*/) * sizeof(float);
   KFAC_CUDA(cudaFuncSetAttribute(jacobi_systolic_kernel<N, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   jacobi_systolic_kernel<N, TB><<<count, TB + N / 2, smem, s>>>(F, n, Q, d, max_sweeps);
   KFAC_LAUNCH_CHECK();
