@@ -10,7 +10,7 @@ namespace kfac {
 // Q: eigenvectors in columns (ld n), d: eigenvalues (unsorted, clamped at 0).
 template <int N, int TB>
 __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_kernel(const float* F, int n, float* Q, float* d,
-                                                                    int max_sweeps) {
+                                                                    int max_sweeps, int fast) {
   using namespace sysj;
   constexpr int h = N / 2, LD = N;
   extern __shared__ float sm[];
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_kernel(const float
   }
   if (tid == 0) { flag[0] = 0; flag[1] = 0; }
   __syncthreads();
-  const Criteria cr{0, 1e-7f, 0.f, 0.f};
+  const Criteria cr{0, 1e-7f, 0.f, 0.f, fast};
   // rot is double buffered by step parity: the crit threads publish the rotations of step t+1
   // while the bulk threads may still be reading those of step t
   int par = 0;
@@ -89,10 +89,11 @@ __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_kernel(const float
 }
 
 template <int N, int TB>
-static int launch_systolic(const float* F, int n, int count, float* Q, float* d, int max_sweeps, cudaStream_t s) {
+static int launch_systolic(const float* F, int n, int count, float* Q, float* d, int max_sweeps, int fast,
+                           cudaStream_t s) {
   const size_t smem = ((size_t)2 * N * N + 2 * N /*rot x2*/ + 4 /*flag*/ + N /*colscale*/) * sizeof(float);
   KFAC_CUDA(cudaFuncSetAttribute(jacobi_systolic_kernel<N, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  jacobi_systolic_kernel<N, TB><<<count, TB + N / 2, smem, s>>>(F, n, Q, d, max_sweeps);
+  jacobi_systolic_kernel<N, TB><<<count, TB + N / 2, smem, s>>>(F, n, Q, d, max_sweeps, fast);
   KFAC_LAUNCH_CHECK();
   return KFAC_OK;
 }
@@ -100,12 +101,13 @@ static int launch_systolic(const float* F, int n, int count, float* Q, float* d,
 }  // namespace kfac
 
 // Not declared in include/kfac_b200.h on purpose (experimental, test-only).
+// flags: bit 0 = fast rotation parameters (sysj::Criteria::fast)
 extern "C" int kfac_experimental_jacobi_systolic(const float* F, int n, int count, float* Q, float* d, int max_sweeps,
-                                                 void* stream) {
+                                                 int flags, void* stream) {
   using namespace kfac;
   KFAC_CHECK_ARG(F && Q && d && n > 0 && n <= 128 && count > 0, "jacobi_systolic arguments");
   if (max_sweeps <= 0) max_sweeps = 24;
   cudaStream_t s = (cudaStream_t)stream;
-  if (n <= 64) return launch_systolic<64, 512>(F, n, count, Q, d, max_sweeps, s);
-  return launch_systolic<128, 960>(F, n, count, Q, d, max_sweeps, s);
+  if (n <= 64) return launch_systolic<64, 512>(F, n, count, Q, d, max_sweeps, flags & 1, s);
+  return launch_systolic<128, 960>(F, n, count, Q, d, max_sweeps, flags & 1, s);
 }

@@ -59,7 +59,25 @@ struct Criteria {
   float tol_in;
   float max_diag;      // block mode: largest squared column norm seen so far
   float nw_ratio;      // block mode: normwise relaxation (see pair_den in eigh.cu)
+  int fast;            // rotation parameters from rsqrt/rcp + one Newton step (short dependent chain)
 };
+
+// 1/sqrt(x) and 1/x to ~1 ulp from the hardware approximations (device) / exact (host emulation)
+KFAC_SYS_HD float rsqrt_refined(float x) {
+#ifdef __CUDA_ARCH__
+  float r = rsqrtf(x);
+  return r * fmaf(-0.5f * x * r, r, 1.5f);
+#else
+  return 1.f / sqrtf(x);
+#endif
+}
+KFAC_SYS_HD float rcp_rn(float x) {
+#ifdef __CUDA_ARCH__
+  return __frcp_rn(x);
+#else
+  return 1.f / x;
+#endif
+}
 
 KFAC_SYS_HD float threshold(const Criteria& cr, float app, float aqq) {
   if (!cr.mode_block) return sqrtf(fabsf(app * aqq));
@@ -71,10 +89,23 @@ KFAC_SYS_HD float threshold(const Criteria& cr, float app, float aqq) {
 KFAC_SYS_HD Rot rotation(const Criteria& cr, float app, float aqq, float apq, int& flags) {
   Rot r{1.f, 0.f};
   if (fabsf(apq) > cr.tol_in * threshold(cr, app, aqq)) {
-    const float tau = (aqq - app) / (2.f * apq);
-    const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-    r.c = 1.f / sqrtf(1.f + t * t);
-    r.s = t * r.c;
+    if (cr.fast) {
+      // t = sign(a b) |b| / (|a| + sqrt(a^2 + b^2)), a = aqq - app, b = 2 apq (scaled by
+      // 1 / max(|a|, |b|) so the squares stay in range): 4 short dependent special-function ops
+      // instead of 5 IEEE div/sqrt -- the chain is the critical path of a step (measured)
+      float a = aqq - app, b = 2.f * apq;
+      const float sc = rcp_rn(fmaxf(fabsf(a), fabsf(b)));
+      a *= sc; b *= sc;
+      const float x = fmaf(a, a, b * b);
+      const float t = copysignf(fabsf(b), (a < 0.f) != (b < 0.f) ? -1.f : 1.f) * rcp_rn(fabsf(a) + x * rsqrt_refined(x));
+      r.c = rsqrt_refined(fmaf(t, t, 1.f));
+      r.s = t * r.c;
+    } else {
+      const float tau = (aqq - app) / (2.f * apq);
+      const float t = copysignf(1.f, tau) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+      r.c = 1.f / sqrtf(1.f + t * t);
+      r.s = t * r.c;
+    }
     if (r.s != 0.f) flags |= 1 | (fabsf(r.s) >= 2e-3f ? 2 : 0);
   }
   return r;

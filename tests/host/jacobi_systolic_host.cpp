@@ -65,7 +65,7 @@ static std::vector<double> ref_eigs(std::vector<double> A, int n) {
 }
 
 template <int N, int TB>
-static void check_solve(unsigned seed, bool graded) {
+static void check_solve(unsigned seed, bool graded, int fast = 0) {
   constexpr int h = N / 2, LD = N;
   std::mt19937 rng(seed);
   std::normal_distribution<float> nd;
@@ -80,7 +80,7 @@ static void check_solve(unsigned seed, bool graded) {
   std::vector<float> M(N * N), W(N * N, 0.f);
   for (int i = 0; i < N * N; ++i) M[i] = (float)M0[i];
   for (int i = 0; i < N; ++i) W[i * LD + i] = 1.f;
-  Criteria cr{0, 1e-7f, 0.f, 0.f};
+  Criteria cr{0, 1e-7f, 0.f, 0.f, fast};
   Rot rot[h], nrot[h];
   std::vector<BulkRegs<N, TB>> regs(TB);
   std::vector<CritRegs> crit(h);
@@ -130,7 +130,7 @@ static void check_solve(unsigned seed, bool graded) {
   std::sort(d.begin(), d.end());
   const std::vector<double> ref = ref_eigs(M0, N);
   double worst_eig = 0; for (int i = 0; i < N; ++i) worst_eig = std::max(worst_eig, std::fabs(d[i] - ref[i]) / mx);
-  std::printf("N=%d TB=%d graded=%d sweeps=%d off=%.2e orth=%.2e resid=%.2e eig=%.2e\n", N, TB, (int)graded, sweeps + 1, worst_off,
+  std::printf("N=%d TB=%d graded=%d fast=%d sweeps=%d off=%.2e orth=%.2e resid=%.2e eig=%.2e\n", N, TB, (int)graded, fast, sweeps + 1, worst_off,
               worst_orth, worst_res, worst_eig);
   CHECK(worst_off < 5e-6, "off-diagonal %.3e", worst_off);
   CHECK(worst_orth < 5e-5, "orthogonality %.3e", worst_orth);
@@ -145,6 +145,9 @@ int main() {
   check_solve<64, 512>(3, false);
   check_solve<64, 512>(4, true);
   check_solve<128, 960>(5, true);
+  check_solve<8, 5>(6, true, 1);
+  check_solve<64, 512>(7, false, 1);
+  check_solve<64, 512>(8, true, 1);
   if (fails) { std::printf("%d failure(s)\n", fails); return 1; }
   std::printf("OK\n");
   return 0;

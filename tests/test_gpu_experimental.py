@@ -12,14 +12,15 @@ pytestmark = [pytest.mark.gpu,
                                  reason='experimental kernels: set KFAC_TEST_EXPERIMENTAL=1')]
 
 
+@pytest.mark.parametrize('flags', [0, 1])
 @pytest.mark.parametrize('n', [64, 100, 128])
-def test_systolic_jacobi_matches_eigh(n):
+def test_systolic_jacobi_matches_eigh(n, flags):
     from kfac_b200 import _cabi
     from test_gpu_kernels import make_psd
     lib = _cabi.load()
     fn = lib.kfac_experimental_jacobi_systolic
     fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     dev = torch.device('cuda:0')
     count = 72
     F = torch.stack([make_psd(n, kind, 11 * i + n) for i, kind in
@@ -28,13 +29,13 @@ def test_systolic_jacobi_matches_eigh(n):
     d = torch.empty(count, n, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
-        assert fn(F.data_ptr(), n, count, Q.data_ptr(), d.data_ptr(), 0, s) == 0, lib.kfac_last_error()
+        assert fn(F.data_ptr(), n, count, Q.data_ptr(), d.data_ptr(), 0, flags, s) == 0, lib.kfac_last_error()
     torch.cuda.synchronize()
     t0 = time.time()
     for _ in range(10):
-        fn(F.data_ptr(), n, count, Q.data_ptr(), d.data_ptr(), 0, s)
+        fn(F.data_ptr(), n, count, Q.data_ptr(), d.data_ptr(), 0, flags, s)
     torch.cuda.synchronize()
-    print(f'systolic n={n} x{count}: {(time.time() - t0) * 100:.3f} ms per launch')
+    print(f'systolic flags={flags} n={n} x{count}: {(time.time() - t0) * 100:.3f} ms per launch')
     F64, Q64, d64 = F.double(), Q.double(), d.double()
     eye = torch.eye(n, device=dev, dtype=torch.float64)
     assert (Q64.transpose(1, 2) @ Q64 - eye).abs().max() < 5e-5
