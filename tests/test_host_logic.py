@@ -221,3 +221,35 @@ def test_systolic_jacobi_host_emulation(tmp_path):
     subprocess.run(['g++', '-O1', '-ffp-contract=off', '-std=c++17', '-I', inc, src, '-o', str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith('OK'), out.stdout[-2000:]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm) prints ONE JSON
+    line with the contract keys; exercised on the small workload so it stays in the CPU budget."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--model', 'resnet32',
+                          '--steps', '1', '--warmup', '0', '--budget-s', '120'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, out.stdout[-1000:]
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['unit'] == 'images/s' and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert d['config']['global_batch'] == 128
+
+
+def test_bench_cpu_arm_other_ranks_exit_quietly():
+    """Under torchrun only rank 0 runs the CPU arm; the other ranks print nothing and exit 0."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2'],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == '', (out.stdout[-500:], out.stderr[-500:])
