@@ -2,6 +2,7 @@
 // exported only through kfac_experimental_jacobi_systolic() so that round 2 can validate and time
 // it against jacobi_smem_kernel before wiring it into the block solver of eigh.cu.
 #include "common.cuh"
+#include "eigh_common.cuh"
 #include "jacobi_systolic.cuh"
 
 namespace kfac {
@@ -95,6 +96,127 @@ static int launch_systolic(const float* F, int n, int count, float* Q, float* d,
   KFAC_CUDA(cudaFuncSetAttribute(jacobi_systolic_kernel<N, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   jacobi_systolic_kernel<N, TB><<<count, TB + N / 2, smem, s>>>(F, n, Q, d, max_sweeps, fast);
   KFAC_LAUNCH_CHECK();
+  return KFAC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block mode: same contract as jacobi_smem_kernel<N> with mode_block = 1 in eigh.cu (one CTA per
+// block pair: Gram M read from and zeroed in the pair buffer, convergence bookkeeping of the
+// matrix, W (mode 3: W^T) written to the pair buffer), with the systolic sweeps in the middle.
+template <int N, int TB>
+__global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_block_kernel(EighMat* mats, const int* list, int max_inner,
+                                                                          int tc_first, int* active_list,
+                                                                          int* active_count, int pair_shift, int fast) {
+  using namespace sysj;
+  constexpr int h = N / 2, LD = N;
+  extern __shared__ float sm[];
+  float* M = sm;
+  float* W = sm + N * N;
+  Rot* rot = reinterpret_cast<Rot*>(W + N * N);     // 2 x h, double buffered by step parity
+  int* flag = reinterpret_cast<int*>(rot + 2 * h);  // 2 words, alternating by sweep
+  __shared__ float redmax[32];
+  const int tid = threadIdx.x, T = TB + h;
+  const bool is_crit = tid >= TB;
+  const int k = tid - TB;
+  EighMat& mt = mats[list[blockIdx.x]];
+  if (mt.done) return;
+  const int local = blockIdx.x + pair_shift - mt.inner_base;
+  float* Mg = mt.M + (int64_t)local * N * N;
+  for (int idx = tid; idx < N * N; idx += T) {
+    M[idx] = Mg[idx];
+    Mg[idx] = 0.f;
+    W[idx] = (idx / N == idx % N) ? 1.f : 0.f;
+  }
+  if (tid == 0) { flag[0] = 0; flag[1] = 0; }
+  __syncthreads();
+  const float tol = mt.tol;
+  {
+    // largest relative off-diagonal of this pair's Gram (convergence measure), as in eigh.cu
+    float dmax = 0.f;
+    for (int j = tid; j < N; j += T) dmax = fmaxf(dmax, M[j * LD + j]);
+    if (dmax > 0.f) atomicMax(&mt.max_diag, __float_as_uint(dmax));
+    const float max_diag = __uint_as_float(mt.max_diag);
+    const float nw_ratio = mt.nw_ratio;
+    float mx = 0.f, ss = 0.f;
+    for (int idx = tid; idx < N * N; idx += T) {
+      const int i = idx / N, j = idx % N;
+      if (j > i) {
+        const float r = rel_off(M[idx], M[i * LD + i], M[j * LD + j], max_diag, nw_ratio);
+        mx = fmaxf(mx, r);
+        ss = fmaf(fminf(r, 1.f), fminf(r, 1.f), ss);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((tid & 31) == 0 && ss > 0.f) atomicAdd(&mt.sweep_sumsq, ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) redmax[tid >> 5] = mx;
+    __syncthreads();
+    if (tid < 32) {
+      float v = (tid < T / 32) ? redmax[tid] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (tid == 0) redmax[0] = v;
+    }
+    __syncthreads();
+    mx = redmax[0];
+    if (tid == 0) {
+      atomicMax(&mt.sweep_off, __float_as_uint(mx));
+      mt.pair_skip[local] = (mx < tol) ? 1 : 0;
+      if (!(mx < tol) && mt.mode == 3 && active_list) active_list[atomicAdd(active_count, 1)] = blockIdx.x - tc_first;
+    }
+    if (mx < tol) return;
+  }
+  const Criteria cr{1, fminf(tol * 0.125f, 1e-6f), __uint_as_float(mt.max_diag), mt.nw_ratio, fast};
+  int par = 0;
+  for (int sweep = 0; sweep < max_inner; ++sweep) {
+    int* fl = flag + (sweep & 1);
+    if (tid == 0) flag[(sweep + 1) & 1] = 0;
+    if (is_crit) {
+      int f = 0;
+      rot[par * h + k] = first_rotation<N, LD>(k, cr, M, f);
+      if (f) atomicOr(fl, f);
+    }
+    __syncthreads();
+    for (int st = 0; st < N - 1; ++st) {
+      const bool more = st < N - 2;
+      const Rot* rcur = rot + par * h;
+      if (!is_crit) {
+        BulkRegs<N, TB> regs;
+        bulk_load<N, LD, TB>(tid, rcur, M, W, regs);
+        asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+        bulk_store<N, LD, TB>(tid, M, W, regs);
+      } else {
+        CritRegs cregs;
+        if (more) crit_load<N, LD>(k, rcur, M, cregs);
+        asm volatile("bar.arrive 1, %0;" ::"r"(T) : "memory");
+        if (more) {
+          int f = 0;
+          rot[(par ^ 1) * h + k] = crit_rotation(cr, cregs, f);
+          if (f) atomicOr(fl, f);
+        }
+      }
+      __syncthreads();
+      par ^= 1;
+    }
+    const int f = *fl;
+    __syncthreads();
+    if (!(f & 1) || !(f & 2)) break;
+  }
+  __syncthreads();
+  float* Wg = mt.W + (int64_t)local * N * N;
+  if (mt.mode == 3) { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[(idx % N) * LD + idx / N]; }   // W^T
+  else { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx]; }
+}
+
+int launch_systolic_block64(EighMat* mats, const int* list, int nblk, int max_inner, int tc_first, int* active_list,
+                            int* active_count, int pair_shift, int fast, cudaStream_t s) {
+  constexpr int N = 64, TB = 512;
+  const size_t smem = ((size_t)2 * N * N + 2 * N /*rot x2*/ + 4 /*flags*/) * sizeof(float);   // 33.3 KB
+  jacobi_systolic_block_kernel<N, TB><<<nblk, TB + N / 2, smem, s>>>(mats, list, max_inner, tc_first, active_list,
+                                                                    active_count, pair_shift, fast);
+  KFAC_CUDA(cudaGetLastError());   // the caller counts the launch
   return KFAC_OK;
 }
 
