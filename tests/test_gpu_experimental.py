@@ -42,3 +42,16 @@ def test_systolic_jacobi_matches_eigh(n, flags):
     rec = Q64 @ torch.diag_embed(d64) @ Q64.transpose(1, 2)
     scale = F64.abs().amax(dim=(1, 2), keepdim=True)
     assert ((rec - F64).abs() / scale).max() < 2e-5
+
+
+@pytest.mark.parametrize('jopt', ['1', '2', '4', '8', '9'])
+def test_eigh_with_experimental_pair_solver(jopt):
+    # KFAC_EIGH_JOPT is read once per process: run the block-solver tests in a child
+    import subprocess
+    import sys
+    env = dict(os.environ, KFAC_EIGH_JOPT=jopt)
+    env.pop('KFAC_TEST_EXPERIMENTAL', None)
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'test_gpu_kernels.py')
+    out = subprocess.run([sys.executable, '-m', 'pytest', here, '-q', '-m', 'gpu', '-x', '-k',
+                          'eigh and not wide', '-p', 'no:cacheprovider'], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
