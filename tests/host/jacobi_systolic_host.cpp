@@ -65,7 +65,7 @@ static std::vector<double> ref_eigs(std::vector<double> A, int n) {
 }
 
 template <int N, int TB>
-static void check_solve(unsigned seed, bool graded, int fast = 0) {
+static void check_solve(unsigned seed, bool graded, int fast = 0, int block_mode = 0) {
   constexpr int h = N / 2, LD = N;
   std::mt19937 rng(seed);
   std::normal_distribution<float> nd;
@@ -81,6 +81,10 @@ static void check_solve(unsigned seed, bool graded, int fast = 0) {
   for (int i = 0; i < N * N; ++i) M[i] = (float)M0[i];
   for (int i = 0; i < N; ++i) W[i * LD + i] = 1.f;
   Criteria cr{0, 1e-7f, 0.f, 0.f, fast};
+  if (block_mode) {   // thresholds of the block solver: tol 3e-6, tol_in = tol / 8, normwise relaxation for n = 4608
+    float md = 0.f; for (int i = 0; i < N; ++i) md = std::fmax(md, M[i * LD + i]);
+    cr = Criteria{1, 3.75e-7f, md, (3e-6f / std::sqrt(4608.f)) / 3e-6f, fast};
+  }
   Rot rot[h], nrot[h];
   std::vector<BulkRegs<N, TB>> regs(TB);
   std::vector<CritRegs> crit(h);
@@ -132,7 +136,7 @@ static void check_solve(unsigned seed, bool graded, int fast = 0) {
   double worst_eig = 0; for (int i = 0; i < N; ++i) worst_eig = std::max(worst_eig, std::fabs(d[i] - ref[i]) / mx);
   std::printf("N=%d TB=%d graded=%d fast=%d sweeps=%d off=%.2e orth=%.2e resid=%.2e eig=%.2e\n", N, TB, (int)graded, fast, sweeps + 1, worst_off,
               worst_orth, worst_res, worst_eig);
-  CHECK(worst_off < 5e-6, "off-diagonal %.3e", worst_off);
+  if (!block_mode) CHECK(worst_off < 5e-6, "off-diagonal %.3e", worst_off);   // (block mode measures against max, not the geometric mean)
   CHECK(worst_orth < 5e-5, "orthogonality %.3e", worst_orth);
   CHECK(worst_res < 2e-5, "residual %.3e", worst_res);
   CHECK(worst_eig < 2e-5, "eigenvalues %.3e", worst_eig);
@@ -145,6 +149,8 @@ int main() {
   check_solve<64, 512>(3, false);
   check_solve<64, 512>(4, true);
   check_solve<128, 960>(5, true);
+  check_solve<64, 512>(9, true, 0, 1);
+  check_solve<64, 512>(10, true, 1, 1);
   check_solve<8, 5>(6, true, 1);
   check_solve<64, 512>(7, false, 1);
   check_solve<64, 512>(8, true, 1);
