@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
   std::vector<float> Q(F.size()), d((size_t)count * n);
   float ms;
   // ---- experimental (flags 0: IEEE rotation chain, 1: fast chain)
-  for (int flags = 0; flags < 2; ++flags) {
+  for (int flags = 0; flags < (n > 64 ? 4 : 2); ++flags) {
     for (int it = 0; it < 3; ++it)
       if (kfac_experimental_jacobi_systolic(dF, n, count, dQ, dD, 0, flags, nullptr)) { std::printf("systolic: %s\n", kfac_last_error()); return 1; }
     CK(cudaDeviceSynchronize());
@@ -64,7 +64,7 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
     std::printf("systolic/%d n=%d x%d: %.1f us per launch\n", flags, n, count, ms * 50);
     CK(cudaMemcpy(Q.data(), dQ, Q.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(d.data(), dD, d.size() * 4, cudaMemcpyDeviceToHost));
-    verify(flags ? "systolic/1" : "systolic/0", F, Q, d, n, count);
+    char tag[32]; std::snprintf(tag, sizeof tag, "systolic/%d", flags); verify(tag, F, Q, d, n, count);
   }
   // ---- product direct mode (jacobi_smem_kernel through kfac_eigh_batched)
   std::vector<kfac_eigh_item> items(count);

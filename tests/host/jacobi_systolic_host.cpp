@@ -149,6 +149,7 @@ int main() {
   check_solve<64, 512>(3, false);
   check_solve<64, 512>(4, true);
   check_solve<128, 960>(5, true);
+  check_solve<128, 480>(11, true);
   check_solve<64, 512>(9, true, 0, 1);
   check_solve<64, 512>(10, true, 1, 1);
   check_solve<8, 5>(6, true, 1);
