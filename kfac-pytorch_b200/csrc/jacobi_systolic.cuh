@@ -140,20 +140,22 @@ KFAC_SYS_HD void bulk_load(int w, const Rot* rot, const float* M, const float* W
 #pragma unroll
   for (int j = 0; j < BulkRegs<N, TB>::MB; ++j) {
     const int idx = w + j * TB;
-    if (idx >= h * h) break;
-    const int b = idx % h, a = idx / h;
-    block_update(rot[a], rot[b], M[a * LD + b], M[a * LD + h + b], M[(h + a) * LD + b], M[(h + a) * LD + h + b],
-                 r.m[j][0], r.m[j][1], r.m[j][2], r.m[j][3]);
+    if (idx < h * h) {   // (guard, not break: keeps the loop unrollable and r.m in registers)
+      const int b = idx % h, a = idx / h;
+      block_update(rot[a], rot[b], M[a * LD + b], M[a * LD + h + b], M[(h + a) * LD + b], M[(h + a) * LD + h + b],
+                   r.m[j][0], r.m[j][1], r.m[j][2], r.m[j][3]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < BulkRegs<N, TB>::WB; ++j) {
     const int idx = w + j * TB;
-    if (idx >= N * h) break;
-    const int k = idx % h, i = idx / h;
-    const Rot q = rot[k];
-    const float u = W[i * LD + k], v = W[i * LD + h + k];
-    r.w[j][0] = q.c * u - q.s * v;
-    r.w[j][1] = q.s * u + q.c * v;
+    if (idx < N * h) {
+      const int k = idx % h, i = idx / h;
+      const Rot q = rot[k];
+      const float u = W[i * LD + k], v = W[i * LD + h + k];
+      r.w[j][0] = q.c * u - q.s * v;
+      r.w[j][1] = q.s * u + q.c * v;
+    }
   }
 }
 
@@ -164,21 +166,23 @@ KFAC_SYS_HD void bulk_store(int w, float* M, float* W, const BulkRegs<N, TB>& r)
 #pragma unroll
   for (int j = 0; j < BulkRegs<N, TB>::MB; ++j) {
     const int idx = w + j * TB;
-    if (idx >= h * h) break;
-    const int b = idx % h, a = idx / h;
-    const int r0 = dest<N>(a), r1 = dest<N>(h + a), c0 = dest<N>(b), c1 = dest<N>(h + b);
-    M[r0 * LD + c0] = r.m[j][0];
-    M[r0 * LD + c1] = r.m[j][1];
-    M[r1 * LD + c0] = r.m[j][2];
-    M[r1 * LD + c1] = r.m[j][3];
+    if (idx < h * h) {
+      const int b = idx % h, a = idx / h;
+      const int r0 = dest<N>(a), r1 = dest<N>(h + a), c0 = dest<N>(b), c1 = dest<N>(h + b);
+      M[r0 * LD + c0] = r.m[j][0];
+      M[r0 * LD + c1] = r.m[j][1];
+      M[r1 * LD + c0] = r.m[j][2];
+      M[r1 * LD + c1] = r.m[j][3];
+    }
   }
 #pragma unroll
   for (int j = 0; j < BulkRegs<N, TB>::WB; ++j) {
     const int idx = w + j * TB;
-    if (idx >= N * h) break;
-    const int k = idx % h, i = idx / h;
-    W[i * LD + dest<N>(k)] = r.w[j][0];
-    W[i * LD + dest<N>(h + k)] = r.w[j][1];
+    if (idx < N * h) {
+      const int k = idx % h, i = idx / h;
+      W[i * LD + dest<N>(k)] = r.w[j][0];
+      W[i * LD + dest<N>(h + k)] = r.w[j][1];
+    }
   }
 }
 
