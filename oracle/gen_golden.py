@@ -132,6 +132,12 @@ def main():
             inv_update_steps={'schedule': [1, 1, 2]})
     fixture('conv_skip', SmallConvNet, conv_batches, 'ce', steps=3, damping=0.003,
             skip_layers=['conv3', 'Linear'])
+    # factors updated in step() instead of in the hooks (base_preconditioner.py:323-333), with
+    # gradient accumulation; and a conv net on a factor/inverse schedule
+    fixture('conv_nohook', SmallConvNet, conv_batches, 'ce', steps=3, micro=2, accumulation_steps=2,
+            damping=0.003, update_factors_in_hook=False)
+    fixture('conv_sched', SmallConvNet, conv_batches, 'ce', steps=6, damping=0.003,
+            factor_update_steps=2, inv_update_steps=4)
 
     # ---- KAISA placement (kfac/assignment.py:227-395)
     ident = lambda ranks: tuple(ranks)  # noqa: E731

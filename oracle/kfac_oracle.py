@@ -199,7 +199,8 @@ class OraclePreconditioner:
                  damping=0.001, factor_decay=0.95, kl_clip=0.001, lr=0.1,
                  accumulation_steps=1, compute_method='eigen',
                  prediv=True, skip_layers=None,
-                 grad_scaler: Callable[[], float] | None = None):
+                 grad_scaler: Callable[[], float] | None = None,
+                 update_factors_in_hook=True):
         import re
         # constants or callables of the step count (base_preconditioner.py:160-213)
         self._factor_update_steps = factor_update_steps
@@ -212,6 +213,7 @@ class OraclePreconditioner:
         self.compute_method = compute_method
         self.prediv = prediv
         self.grad_scaler = grad_scaler
+        self.update_factors_in_hook = update_factors_in_hook
         self.steps = 0
         self.mini = {}
         self.layers: dict[torch.nn.Module, OracleLayer] = {}
@@ -240,7 +242,7 @@ class OraclePreconditioner:
         L.a_batch = a if L.a_batch is None else L.a_batch + a
         L.a_count += 1
         self.mini[L.name] = self.mini.get(L.name, 0) + 1
-        if self.mini[L.name] % self.accumulation_steps == 0:
+        if self.update_factors_in_hook and self.mini[L.name] % self.accumulation_steps == 0:
             L.A = ema_update(L.A, L.a_batch, L.a_count, self.factor_decay)
             L.a_batch, L.a_count = None, 0
 
@@ -255,13 +257,23 @@ class OraclePreconditioner:
         g = L.g_factor_of(g)
         L.g_batch = g if L.g_batch is None else L.g_batch + g
         L.g_count += 1
-        if self.mini.get(L.name, 0) % self.accumulation_steps == 0:
+        if self.update_factors_in_hook and self.mini.get(L.name, 0) % self.accumulation_steps == 0:
             L.G = ema_update(L.G, L.g_batch, L.g_count, self.factor_decay)
             L.g_batch, L.g_count = None, 0
 
     @torch.no_grad()
     def step(self):
         layers = list(reversed(list(self.layers.values())))
+        # factors updated here instead of in the hooks (base_preconditioner.py:323-333)
+        if not self.update_factors_in_hook and self.steps % self.factor_update_steps == 0:
+            for L in layers:
+                self.mini[L.name] = 0
+                if L.a_count:
+                    L.A = ema_update(L.A, L.a_batch, L.a_count, self.factor_decay)
+                    L.a_batch, L.a_count = None, 0
+                if L.g_count:
+                    L.G = ema_update(L.G, L.g_batch, L.g_count, self.factor_decay)
+                    L.g_batch, L.g_count = None, 0
         if self.steps % self.inv_update_steps == 0:
             for L in layers:
                 if self.compute_method == 'eigen':

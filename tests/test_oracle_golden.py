@@ -6,10 +6,10 @@ import os
 import pytest
 import torch
 
-from conftest import GOLDEN, GOLDEN_NAMES, rel_fro, replay
+from conftest import GOLDEN, GOLDEN_CPU_ONLY, GOLDEN_NAMES, rel_fro, replay
 from oracle import kfac_oracle as O
 
-NAMES = list(GOLDEN_NAMES)
+NAMES = list(GOLDEN_NAMES) + list(GOLDEN_CPU_ONLY)
 
 
 def test_get_cov_reference_vectors():
