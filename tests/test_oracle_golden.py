@@ -85,3 +85,40 @@ def test_oracle_matches_distributed_reference(name):
             for p in model.parameters():
                 p -= fx['lr_sgd'] * p.grad
     print(name, 'worst rel-fro oracle(concatenated batch) vs distributed reference', worst)
+
+
+def test_oracle_operators_match_their_definitions():
+    """Independent of the reference: the two K-FAC operators of the path as dense linear algebra
+    (SURVEY.md App. A.11).  eigen = (G (x) A + damping I)^-1 vec(grad); inverse =
+    (G + damping I)^-1 grad (A + damping I)^-1; conv factor scaling A = P^T P / (B S^3)."""
+    torch.manual_seed(5)
+    g, a, damping = 4, 6, 0.05
+    xa, xg = torch.randn(20, a, dtype=torch.float64), torch.randn(20, g, dtype=torch.float64)
+    A, G = (xa.t() @ xa / 20).float(), (xg.t() @ xg / 20).float()
+    grad = torch.randn(g, a)
+    da, qa = O.eigen_decompose(A)
+    dg, qg = O.eigen_decompose(G)
+    # row-major vec(grad): (G kron A) vec(X) = vec(G X A^T)
+    K = torch.kron(G.double(), A.double()) + damping * torch.eye(g * a, dtype=torch.float64)
+    want = torch.linalg.solve(K, grad.double().reshape(-1)).reshape(g, a)
+    got = O.precondition_eigen(grad, qa, qg, dgda=O.eigen_dgda(dg, da, damping))
+    assert rel_fro(got, want) < 1e-5
+    got2 = O.precondition_eigen(grad, qa, qg, da=da, dg=dg, damping=damping)
+    assert rel_fro(got2, want) < 1e-5
+    want_inv = torch.linalg.inv(G.double() + damping * torch.eye(g, dtype=torch.float64)) @ grad.double() @ \
+        torch.linalg.inv(A.double() + damping * torch.eye(a, dtype=torch.float64))
+    got_inv = O.precondition_inverse(grad, O.damped_inverse(A, damping), O.damped_inverse(G, damping))
+    assert rel_fro(got_inv, want_inv) < 1e-5
+    # conv A-factor: patches (B, Ho, Wo, C kh kw) with a ones column, scaled 1 / S before the covariance
+    x = torch.randn(2, 3, 5, 5)
+    pt = torch.nn.functional.unfold(x, (3, 3), padding=1, stride=2)        # (B, C kh kw, S)
+    B_, S = 2, pt.shape[-1]
+    P = torch.cat([pt.transpose(1, 2).reshape(B_ * S, -1), torch.ones(B_ * S, 1)], 1)
+    want_a = P.t() @ P / (B_ * S ** 3)
+    got_a = O.conv2d_a_factor(x, (3, 3), (2, 2), (1, 1), True)
+    assert rel_fro(got_a, want_a) < 1e-5
+    # kl-clip scale
+    P1 = [torch.randn(3, 5)]
+    G1 = [torch.randn(3, 5)]
+    vg = float((P1[0] * G1[0]).sum()) * 0.1 ** 2
+    assert abs(O.grad_scale(P1, G1, 0.1, 0.001) - min(1.0, (0.001 / abs(vg)) ** 0.5)) < 1e-6
