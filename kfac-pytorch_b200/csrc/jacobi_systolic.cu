@@ -223,7 +223,8 @@ int launch_systolic_block64(EighMat* mats, const int* list, int nblk, int max_in
 }  // namespace kfac
 
 // Not declared in include/kfac_b200.h on purpose (experimental, test-only).
-// flags: bit 0 = fast rotation parameters (sysj::Criteria::fast); bit 1 = n > 64 with 480 + 64 threads
+// flags: bits 0 and 2 = rotation chain (0: IEEE, 1: sysj::Criteria::fast = 1, 4: fast = 2, half-angle form);
+// bit 1 = n > 64 with 480 + 64 threads
 // (no register spills, more work per thread) instead of 960 + 64
 extern "C" int kfac_experimental_jacobi_systolic(const float* F, int n, int count, float* Q, float* d, int max_sweeps,
                                                  int flags, void* stream) {
@@ -231,7 +232,7 @@ extern "C" int kfac_experimental_jacobi_systolic(const float* F, int n, int coun
   KFAC_CHECK_ARG(F && Q && d && n > 0 && n <= 128 && count > 0, "jacobi_systolic arguments");
   if (max_sweeps <= 0) max_sweeps = 24;
   cudaStream_t s = (cudaStream_t)stream;
-  if (n <= 64) return launch_systolic<64, 512>(F, n, count, Q, d, max_sweeps, flags & 1, s);
-  if (flags & 2) return launch_systolic<128, 480>(F, n, count, Q, d, max_sweeps, flags & 1, s);
-  return launch_systolic<128, 960>(F, n, count, Q, d, max_sweeps, flags & 1, s);
+  if (n <= 64) return launch_systolic<64, 512>(F, n, count, Q, d, max_sweeps, (flags & 4) ? 2 : (flags & 1), s);
+  if (flags & 2) return launch_systolic<128, 480>(F, n, count, Q, d, max_sweeps, (flags & 4) ? 2 : (flags & 1), s);
+  return launch_systolic<128, 960>(F, n, count, Q, d, max_sweeps, (flags & 4) ? 2 : (flags & 1), s);
 }

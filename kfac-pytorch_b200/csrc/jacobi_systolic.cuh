@@ -59,7 +59,7 @@ struct Criteria {
   float tol_in;
   float max_diag;      // block mode: largest squared column norm seen so far
   float nw_ratio;      // block mode: normwise relaxation (see pair_den in eigh.cu)
-  int fast;            // rotation parameters from rsqrt/rcp + one Newton step (short dependent chain)
+  int fast;            // 1: rotation parameters from rsqrt/rcp + one Newton step; 2: half-angle form (2 rsqrt)
 };
 
 // 1/sqrt(x) and 1/x to ~1 ulp from the hardware approximations (device) / exact (host emulation)
@@ -89,7 +89,22 @@ KFAC_SYS_HD float threshold(const Criteria& cr, float app, float aqq) {
 KFAC_SYS_HD Rot rotation(const Criteria& cr, float app, float aqq, float apq, int& flags) {
   Rot r{1.f, 0.f};
   if (fabsf(apq) > cr.tol_in * threshold(cr, app, aqq)) {
-    if (cr.fast) {
+    if (cr.fast == 2) {
+      // half-angle form, two dependent special-function ops: with a = aqq - app, b = 2 apq and
+      // h = sqrt(a^2 + b^2):  cos 2t = |a| / h,  c = sqrt((1 + cos 2t) / 2),  s = sign(a b) |b| / (2 h c)
+      // (no cancellation: small angles give s ~ b / (2 |a|) by multiplication).  The operands are
+      // scaled by a power of two taken from the exponent of max(|a|, |b|) -- no reciprocal.
+      float a = aqq - app, b = 2.f * apq;
+      const float mxv = fmaxf(fabsf(a), fabsf(b));
+      int e;
+      (void)frexpf(mxv, &e);
+      a = ldexpf(a, -e); b = ldexpf(b, -e);
+      const float rh = rsqrt_refined(fmaf(a, a, b * b));        // 1 / h
+      const float cc = fmaf(0.5f * fabsf(a), rh, 0.5f);         // c^2 in [0.5, 1]
+      const float rc = rsqrt_refined(cc);                        // 1 / c
+      r.c = cc * rc;
+      r.s = copysignf(0.5f * fabsf(b) * rh * rc, (a < 0.f) != (b < 0.f) ? -1.f : 1.f);
+    } else if (cr.fast) {
       // t = sign(a b) |b| / (|a| + sqrt(a^2 + b^2)), a = aqq - app, b = 2 apq (scaled by
       // 1 / max(|a|, |b|) so the squares stay in range): 4 short dependent special-function ops
       // instead of 5 IEEE div/sqrt -- the chain is the critical path of a step (measured)

@@ -55,7 +55,9 @@ int main(int argc, char** argv) {
   std::vector<float> Q(F.size()), d((size_t)count * n);
   float ms;
   // ---- experimental (flags 0: IEEE rotation chain, 1: fast chain)
-  for (int flags = 0; flags < (n > 64 ? 4 : 2); ++flags) {
+  for (int flags = 0; flags < 8; ++flags) {
+    if (n <= 64 && (flags & 2)) continue;   // bit 1 only matters for n > 64
+    if ((flags & 5) == 5) continue;          // bits 0 and 2 are alternatives
     for (int it = 0; it < 3; ++it)
       if (kfac_experimental_jacobi_systolic(dF, n, count, dQ, dD, 0, flags, nullptr)) { std::printf("systolic: %s\n", kfac_last_error()); return 1; }
     CK(cudaDeviceSynchronize());

@@ -153,6 +153,9 @@ int main() {
   check_solve<64, 512>(9, true, 0, 1);
   check_solve<64, 512>(10, true, 1, 1);
   check_solve<8, 5>(6, true, 1);
+  check_solve<64, 512>(12, false, 2);
+  check_solve<64, 512>(13, true, 2);
+  check_solve<64, 512>(14, true, 2, 1);
   check_solve<64, 512>(7, false, 1);
   check_solve<64, 512>(8, true, 1);
   if (fails) { std::printf("%d failure(s)\n", fails); return 1; }

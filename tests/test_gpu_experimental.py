@@ -12,7 +12,7 @@ pytestmark = [pytest.mark.gpu,
                                  reason='experimental kernels: set KFAC_TEST_EXPERIMENTAL=1')]
 
 
-@pytest.mark.parametrize('flags', [0, 1])
+@pytest.mark.parametrize('flags', [0, 1, 4])
 @pytest.mark.parametrize('n', [64, 100, 128])
 def test_systolic_jacobi_matches_eigh(n, flags):
     from kfac_b200 import _cabi
