@@ -167,7 +167,10 @@ __global__ void __launch_bounds__(256) eigh_gram_kernel(EighMat* mats, const int
 //   bit 2  fewer shared-memory instructions per step (the kernel is bound by them: ~56 LDS/STS per
 //          thread and step): (c, s, p, q) of a rotation packed into one float4, and only the upper
 //          triangle of M is kept up to date (block pairs a <= b)
-template <int N, int OPT = 0>
+//   SORT   block mode: the columns of W are written in the order of decreasing new squared column norm
+//          (de Rijk's ordering carried through the pairs: the block solver's columns become sorted by
+//          eigenvalue, which brings the quadratic phase forward -- numpy model: 7-9 -> 5-7 sweeps)
+template <int N, int OPT = 0, bool SORT = false>
 __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const int* list,
                                                            int mode_block, int max_inner,
                                                            int tc_first = 0, int* active_list = nullptr,
@@ -378,6 +381,19 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
 
   if (mode_block) {
     float* Wg = mt.W + (int64_t)local * N * N;
+    if (SORT) {
+      // perm[r] = column with the r-th largest rotated diagonal entry (ties by index)
+      __shared__ int sperm[N];
+      for (int j = tid; j < N; j += T) {
+        const float dj = M[j][j];
+        int r = 0;
+        for (int k2 = 0; k2 < N; ++k2) { const float dk = M[k2][k2]; r += (dk > dj) || (dk == dj && k2 < j); }
+        sperm[r] = j;
+      }
+      __syncthreads();
+      if (mt.mode == 3) { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx % N][sperm[idx / N]]; }   // W^T
+      else { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx / N][sperm[idx % N]]; }
+    } else
     if (mt.mode == 3) { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx % N][idx / N]; }   // W^T
     else { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx / N][idx % N]; }
   } else {
@@ -1001,18 +1017,27 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
         }
         if (!wide) {
           // experimental inner-solver variants (see jacobi_smem_kernel): KFAC_EIGH_JOPT = bit mask 1 | 2 | 4;
-          // 8 (+1) = the data-moving solver of jacobi_systolic.cu (with the fast rotation chain)
+          // 8 (+1) = the data-moving solver of jacobi_systolic.cu (with the fast rotation chain);
+          // 16 = pair columns written sorted by their new norm (combines with 0, 1, 8, 9)
           static const int jopt_all = getenv("KFAC_EIGH_JOPT") ? atoi(getenv("KFAC_EIGH_JOPT")) : 0;
           const int jopt = jopt_all & 7;
           const bool jopt8 = (jopt_all & 8) != 0;
+          const bool jsort = (jopt_all & 16) != 0;   // sorted pair columns (with jopt 0 / 1, or with the systolic solver)
           const int nblk = pl.total_pairs + pl.tc_pairs;
 #define KFAC_JACOBI_BLOCK(OPT)                                                                              \
   jacobi_smem_kernel<64, OPT><<<nblk, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps, pl.total_pairs, \
                                                         d_active_list, d_active_count, 0)
           if (jopt8) {   // experimental data-moving pair solver (jacobi_systolic.cu)
             const int rc = launch_systolic_block64(d_mats, d_all_pair, nblk, inner_sweeps, pl.total_pairs, d_active_list,
-                                                   d_active_count, 0, jopt & 1, s);
+                                                   d_active_count, 0, (jopt & 1) | (jsort ? 2 : 0), s);
             if (rc) return rc;
+          } else if (jsort) {
+            if (jopt & 1)
+              jacobi_smem_kernel<64, 1, true><<<nblk, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps, pl.total_pairs,
+                                                                      d_active_list, d_active_count, 0);
+            else
+              jacobi_smem_kernel<64, 0, true><<<nblk, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps, pl.total_pairs,
+                                                                      d_active_list, d_active_count, 0);
           } else
           switch (jopt) {
             case 1: KFAC_JACOBI_BLOCK(1); break;

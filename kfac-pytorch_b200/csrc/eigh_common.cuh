@@ -67,8 +67,8 @@ __device__ __forceinline__ float rel_off(float apq, float app, float aqq, float 
 }
 
 // experimental block-mode pair solver (jacobi_systolic.cu), selected by KFAC_EIGH_JOPT bit 3;
-// same contract as jacobi_smem_kernel<64> in block mode (fast: rsqrt/rcp rotation chain)
+// same contract as jacobi_smem_kernel<64> in block mode (opts bit 0: rsqrt/rcp rotation chain, bit 1: sorted columns)
 int launch_systolic_block64(EighMat* mats, const int* list, int nblk, int max_inner, int tc_first, int* active_list,
-                            int* active_count, int pair_shift, int fast, cudaStream_t s);
+                            int* active_count, int pair_shift, int opts, cudaStream_t s);
 
 }  // namespace kfac

@@ -106,9 +106,10 @@ static int launch_systolic(const float* F, int n, int count, float* Q, float* d,
 template <int N, int TB>
 __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_block_kernel(EighMat* mats, const int* list, int max_inner,
                                                                           int tc_first, int* active_list,
-                                                                          int* active_count, int pair_shift, int fast) {
+                                                                          int* active_count, int pair_shift, int opts) {
   using namespace sysj;
   constexpr int h = N / 2, LD = N;
+  const int fast = opts & 1;
   extern __shared__ float sm[];
   float* M = sm;
   float* W = sm + N * N;
@@ -206,16 +207,29 @@ __global__ void __launch_bounds__(TB + N / 2) jacobi_systolic_block_kernel(EighM
   }
   __syncthreads();
   float* Wg = mt.W + (int64_t)local * N * N;
+  if (opts & 2) {   // columns in the order of decreasing new squared norm (see jacobi_smem_kernel SORT)
+    __shared__ int sperm[N];
+    for (int j = tid; j < N; j += T) {
+      const float dj = M[j * LD + j];
+      int r = 0;
+      for (int k2 = 0; k2 < N; ++k2) { const float dk = M[k2 * LD + k2]; r += (dk > dj) || (dk == dj && k2 < j); }
+      sperm[r] = j;
+    }
+    __syncthreads();
+    if (mt.mode == 3) { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[(idx % N) * LD + sperm[idx / N]]; }
+    else { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[(idx / N) * LD + sperm[idx % N]]; }
+    return;
+  }
   if (mt.mode == 3) { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[(idx % N) * LD + idx / N]; }   // W^T
   else { for (int idx = tid; idx < N * N; idx += T) Wg[idx] = W[idx]; }
 }
 
 int launch_systolic_block64(EighMat* mats, const int* list, int nblk, int max_inner, int tc_first, int* active_list,
-                            int* active_count, int pair_shift, int fast, cudaStream_t s) {
+                            int* active_count, int pair_shift, int opts, cudaStream_t s) {
   constexpr int N = 64, TB = 512;
   const size_t smem = ((size_t)2 * N * N + 2 * N /*rot x2*/ + 4 /*flags*/) * sizeof(float);   // 33.3 KB
   jacobi_systolic_block_kernel<N, TB><<<nblk, TB + N / 2, smem, s>>>(mats, list, max_inner, tc_first, active_list,
-                                                                    active_count, pair_shift, fast);
+                                                                    active_count, pair_shift, opts);
   KFAC_CUDA(cudaGetLastError());   // the caller counts the launch
   return KFAC_OK;
 }

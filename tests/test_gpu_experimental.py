@@ -44,7 +44,7 @@ def test_systolic_jacobi_matches_eigh(n, flags):
     assert ((rec - F64).abs() / scale).max() < 2e-5
 
 
-@pytest.mark.parametrize('jopt', ['1', '2', '4', '8', '9'])
+@pytest.mark.parametrize('jopt', ['1', '2', '4', '8', '9', '16', '17', '24', '25'])
 def test_eigh_with_experimental_pair_solver(jopt):
     # KFAC_EIGH_JOPT is read once per process: run the block-solver tests in a child
     import subprocess
