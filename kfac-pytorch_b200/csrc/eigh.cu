@@ -797,6 +797,7 @@ static int eigh_set_attrs() {   // once, from the calling thread, before any wor
   static bool done = false;
   if (done) return KFAC_OK;
   KFAC_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM128));
+  KFAC_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<128, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM128));
   KFAC_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM64));
   KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicyT<true>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
   KFAC_CUDA(cudaFuncSetAttribute(tc::pipeline_kernel<GramPolicyT<false>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PSMEM));
@@ -1052,10 +1053,16 @@ static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
 #undef KFAC_JACOBI_BLOCK
           count_launch(1);
         } else {   // 64x64 problems of the SIMT class, 128x128 problems of the tensor-core class
+          static const bool wsort = getenv("KFAC_EIGH_JOPT") && (atoi(getenv("KFAC_EIGH_JOPT")) & 16);   // sorted pair columns
           if (pl.total_pairs > 0) {
-            jacobi_smem_kernel<64><<<pl.total_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps);
+            if (wsort) jacobi_smem_kernel<64, 0, true><<<pl.total_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps);
+            else jacobi_smem_kernel<64><<<pl.total_pairs, 512, SMEM64, s>>>(d_mats, d_all_pair, 1, inner_sweeps);
             count_launch(1);
           }
+          if (wsort)
+            jacobi_smem_kernel<128, 0, true><<<pl.tc_pairs, 1024, SMEM128, s>>>(d_mats, d_all_pair + pl.total_pairs, 1, inner_sweeps,
+                                                                                0, d_active_list, d_active_count, pl.total_pairs);
+          else
           jacobi_smem_kernel<128><<<pl.tc_pairs, 1024, SMEM128, s>>>(d_mats, d_all_pair + pl.total_pairs, 1, inner_sweeps, 0,
                                                                      d_active_list, d_active_count, pl.total_pairs);
           count_launch(1);
