@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(N * 8) jacobi_smem_kernel(EighMat* mats, const
   int* pq = reinterpret_cast<int*>(cs + N);   // (p,q) of every pair of the current step
   if (OPT & 2) __syncthreads();
   const bool bip_first = (OPT & 2) && mode_block && !sh_within;
-  for (int sweep = 0; sweep < max_inner + (bip_first ? 1 : 0); ++sweep) {
+  for (int sweep = 0; sweep < max_inner; ++sweep) {   // OPT bit 1: the bipartite sweep counts as one of them
     int rotated_sweep = 0;
     if (tid == 0) sh_big = 0;   // set when some |sin| >= 2e-3 in this sweep
     __syncthreads();
