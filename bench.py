@@ -31,6 +31,7 @@ import torch.distributed as dist  # noqa: E402
 
 warnings.filterwarnings('ignore', message='Full backward hook is firing')
 
+EIGH_KERNEL_NOTE = '(see DESIGN.md 3)'
 METRIC = 'images/sec ResNet-50 K-FAC training step (fwd+bwd+factor hooks+preconditioner.step()+SGD), factor=inv=1'
 
 
@@ -48,12 +49,16 @@ def parse():
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default 32 / 128)')
     ap.add_argument('--grad-worker-fraction', type=float, default=-1.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--batches', type=int, default=8, help='distinct pre-generated batches cycled through (>= 8: every '
+                    'step sees new statistics; 1 = the stationary-input number of round 1)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the untimed parity step after the timed region')
+    ap.add_argument('--no-stationary', action='store_true', help='skip the extra stationary-input timing')
     ap.add_argument('--budget-s', type=float, default=240.0, help='reference arm wall-clock budget')
     return ap.parse_args()
 
 
 def make_workload(name, batch):
-    from oracle.models import resnet32, resnet50
+    from workloads import resnet32, resnet50
     if name == 'resnet50':
         b = batch or 32
         return resnet50, (b, 3, 224, 224), 1000, dict(damping=0.001, factor_decay=0.95, kl_clip=0.001, lr=0.1), \
@@ -183,6 +188,56 @@ def tc_gemm_microbench(lib, dev, n=4096, iters=10):
 
 
 # ------------------------------------------------------------------ own arm
+def parity_step(pre, model, world, rank, dev, hp):
+    """One UNTIMED step after the timed region, checked against the CPU oracle (test infrastructure used as
+    the checker only; nothing here is timed or shipped).  ResNets hold BatchNorm, so the concatenated-batch
+    equivalence of tests/dist_parity.py does not apply; instead:
+      C1   the all-reduced factor arena must equal the mean over ranks of the local (pre-reduce) arenas;
+      K5-K12 + C2 + C3   rank 0 recomputes, on the host with the oracle's operators, the preconditioned gradient
+           of EVERY layer from the all-reduced factors and the DDP-averaged raw gradients, and compares it with
+           the P this rank holds after step() (computed here or received from its KAISA source);
+      all ranks must end the step with identical final gradients."""
+    from oracle import kfac_oracle as O
+    out = {}
+    layers = [l for _, l in pre._layers.values()]
+    raw = [O.grad_matrix(l.module.get_weight_grad().detach().float().cpu(),
+                         l.module.get_bias_grad().detach().float().cpu() if l.module.has_bias() else None)
+           for l in layers] if rank == 0 else None
+    pre._flush_factor_updates()
+    if world > 1:
+        local = pre._factor_arena.clone()
+        dist.all_reduce(local)
+        local /= world
+    pre.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        err = float((pre._factor_arena - local).norm() / local.norm())
+        out['factor_allreduce_rel_err'] = err
+        del local
+        worst = torch.zeros(1, device=dev)
+        for p in model.parameters():
+            ref = p.grad.clone()
+            dist.broadcast(ref, src=0)
+            worst = torch.maximum(worst, (p.grad - ref).norm() / ref.norm().clamp_min(1e-30))
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        out['final_grad_rank_spread'] = float(worst.item())
+    if rank == 0:
+        torch.set_num_threads(usable_cores())
+        damping = float(hp['damping'])
+        worst, worst_layer = 0.0, None
+        for l, g in zip(layers, raw):
+            da, qa = O.eigen_decompose(l.a_factor.detach().float().cpu())
+            dg, qg = O.eigen_decompose(l.g_factor.detach().float().cpu())
+            want = O.precondition_eigen(g, qa, qg, dgda=O.eigen_dgda(dg, da, damping)).double()
+            got = l._p_view.detach().double().cpu()
+            e = float((got - want).norm() / want.norm())
+            if e > worst:
+                worst, worst_layer = e, (l.a_dim, l.g_dim)
+        out.update({'worst_layer_P_rel_fro_vs_oracle': worst, 'worst_layer_dims_a_g': worst_layer,
+                    'layers_checked': len(layers), 'bar': 1e-3, 'ok': bool(worst < 1e-3)})
+    return out
+
+
 def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -209,19 +264,42 @@ def run_b200(args):
     crit = torch.nn.CrossEntropyLoss()
     timer = PhaseTimer(pre)
 
+    # NB distinct pre-generated batches, cycled: every step sees new statistics (a single repeated batch lets a
+    # warm-started iterative eigensolver converge in 1-3 sweeps, which the CPU arm's LAPACK cost does not see)
     torch.manual_seed(1 + rank)
     B = shape[0]
-    host_x = torch.randn(*shape).pin_memory()
-    host_y = torch.randint(0, classes, (B,)).pin_memory()
-    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
+    NB = max(1, args.batches)
+    host = [(torch.randn(*shape).pin_memory(), torch.randint(0, classes, (B,)).pin_memory()) for _ in range(NB)]
+    devb = [(x.to(dev), y.to(dev)) for x, y in host]
     loss_host = torch.zeros(1).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_bytes = host[0][0].numel() * 4 + host[0][1].numel() * 8
+    counter = {'i': 0}
 
-    def one_step(e2e):
+    def stage(i):
+        """Issue the H2D copy of batch i on the copy stream (double-buffered prefetch, like a data loader
+        worker): returns (x, y, event)."""
+        hx, hy = host[i % NB]
+        with torch.cuda.stream(copy_stream):
+            x = hx.to(dev, non_blocking=True)
+            y = hy.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return x, y, ev
+
+    def one_step(e2e, staged=None, prefetch=False, stationary=False):
+        i = counter['i']
+        counter['i'] += 1
+        nxt = None
         if e2e:
-            x = host_x.to(dev, non_blocking=True)
-            y = host_y.to(dev, non_blocking=True)
+            x, y, ev = staged if staged is not None else stage(i)
+            torch.cuda.current_stream().wait_event(ev)
+            x.record_stream(torch.cuda.current_stream())
+            y.record_stream(torch.cuda.current_stream())
+            if prefetch:
+                nxt = stage(i + 1)        # overlaps with this step's compute
         else:
-            x, y = dev_x, dev_y
+            x, y = devb[0] if stationary else devb[i % NB]
         opt.zero_grad(set_to_none=True)
         loss = crit(model(x), y)
         loss.backward()
@@ -229,20 +307,22 @@ def run_b200(args):
         opt.step()
         if e2e:
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        return loss
+        return nxt
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_loop(n, e2e):
+    def timed_loop(n, e2e, stationary=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.kfac_launch_count()
         e0.record()
-        for _ in range(n):
-            one_step(e2e)
+        staged = None
+        for k in range(n):
+            # exactly n H2D copies inside the region: step k waits for its own batch and prefetches batch k+1
+            staged = one_step(e2e, staged=staged, prefetch=(k + 1 < n), stationary=stationary)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -250,7 +330,8 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), lib.kfac_launch_count() - l0
 
-    for _ in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         one_step(False)
     barrier()
     sampler = ClockSampler(local)
@@ -261,6 +342,20 @@ def run_b200(args):
     phase_ms = timer.totals_ms()
     ms_e2e, _ = timed_loop(args.steps, True)
     clocks = sampler.stop()
+    # extra keys (not the headline): the stationary-input number of round 1 (same batch every step) and the raw
+    # host->device bandwidth of this box (explains value vs e2e when the PCIe path is slow)
+    ms_stat = None
+    if not args.no_stationary:
+        for _ in range(2):
+            one_step(False, stationary=True)
+        ms_stat, _ = timed_loop(max(3, args.steps // 2), False, stationary=True)
+        ms_stat /= max(3, args.steps // 2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        host[0][0].to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * host[0][0].numel() * 4 / (time.perf_counter() - t0) / 1e9
 
     K = args.steps
     imgs = B * world * K
@@ -278,42 +373,59 @@ def run_b200(args):
     # KAISA share, the roofline line is reported for rank 0's local phase time.
     inv_ms = phase_ms.get('compute_inverses', 0.0) / K
     my_eig = 0.0
+    my_bytes = 0.0
     r = rank
     for name, l in pre._layers.values():
         if pre._assignment.inv_worker(name, 'A') == r:
             my_eig += 9.0 * l.a_dim ** 3
+            my_bytes += 12.0 * l.a_dim ** 2
         if pre._assignment.inv_worker(name, 'G') == r:
             my_eig += 9.0 * l.g_dim ** 3
+            my_bytes += 12.0 * l.g_dim ** 2
     achieved = (my_eig / (inv_ms / 1e3) / 1e12) if inv_ms > 0 else 0.0
     gemm_tf, gemm_ms = tc_gemm_microbench(lib, dev) if rank == 0 else (0.0, 0.0)
     burst_peak = float(peaks.get('bf16_tflops', 1590.0))
+    traffic = None
+    try:   # dram bytes per kfac_eigh_batched call, from the committed ncu capture of this command (N = 1)
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'eigh_traffic.json')))
+        if world == 1 and tr.get('model') == args.model:
+            traffic = tr.get('dram_bytes_per_call')
+    except Exception:  # noqa: BLE001
+        pass
     out = {
         'metric': metric_name(args.model), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / K, 'higher_is_better': True,
+        'warmup': W, 'ms_per_step': ms_dev / K, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (model fwd/bwd fp32; K-FAC path fp32)',
         'data': 'synthetic',
         'config': {'workload': wl, 'global_batch': B * world, 'grad_worker_fraction': frac,
-                   'parallelism': f'dp{world}', 'l2': 'inputs+factors >> 126 MB L2 (activations 1.4 GB, factors 615 MB)'},
+                   'parallelism': f'dp{world}', 'distinct_batches': NB,
+                   'l2': 'inputs+factors >> 126 MB L2 (activations 1.4 GB, factors 615 MB)'},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': ms_e2e / K,
-                'h2d_bytes_per_step': host_x.numel() * 4 + host_y.numel() * 8, 'd2h_bytes_per_step': 4},
+                'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                'how': 'pinned-host batch -> device every step on a copy stream (batch k+1 prefetched under the compute '
+                       'of step k, every copy inside the timed region), loss read back to pinned host memory',
+                'h2d_gb_per_s_this_box': h2d_gbs},
         'gpu_launches': int(launches),
         'kfac_phase_ms_per_step': {k: v / K for k, v in sorted(phase_ms.items())},
         # preconditioner.step() itself (BASELINE.json: "K-FAC step() ms"): the phases step() runs, without the
         # factor hooks that run inside forward/backward
         'kfac_step_ms': sum(v for k, v in phase_ms.items() if k not in ('factor_a', 'factor_g')) / K,
         'kfac_hooks_ms': sum(v for k, v in phase_ms.items() if k in ('factor_a', 'factor_g')) / K,
+        'stationary_input': ({'ms_per_step': ms_stat, 'value': B * world / (ms_stat / 1e3),
+                              'note': 'same batch every step (round-1 protocol); not the headline'}
+                             if ms_stat else None),
         # dominant launch of the step: ONE kfac_eigh_batched call (all factors this rank owns), timed
         # live in the timed region with CUDA events on the launching stream
-        'roofline': {'kernel': 'kfac_eigh_batched (block one-sided Jacobi rounds: tcgen05 Gram -> smem Jacobi '
-                               '-> tcgen05 apply), one call per step over all factors of this rank',
+        'roofline': {'kernel': 'kfac_eigh_batched: one call per step over all factors of this rank '
+                               + EIGH_KERNEL_NOTE,
                      'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak, 'unit': 'TFLOP/s',
-                     'frac': achieved / tensor_peak if tensor_peak else None, 'traffic': None,
+                     'frac': achieved / tensor_peak if tensor_peak else None, 'traffic': traffic,
+                     'algorithmic_bytes': my_bytes,
                      'ms_per_launch': inv_ms,
                      'convention': 'algorithmic 9 n^3 flop per eigendecomposition (SURVEY.md 8d) summed over the '
-                                   "rank's factors / CUDA-event time of the call; the Jacobi rounds execute ~12 n^3 "
-                                   'flop per sweep as 3xTF32 MMAs and are latency/HBM bound (profiles/r01_ncu_full_pipeline.md: '
-                                   'Gram launch 88.9 MB DRAM traffic, tensor pipe 53 % active)',
+                                   "rank's factors / CUDA-event time of the call; algorithmic bytes 3*4*n^2 per factor; "
+                                   'traffic = dram__bytes_read+write of all kernels of one call (profiles/eigh_traffic.json)',
                      'peak_source': peak_src},
         # the GEMM engine all tensor-core kernels instantiate, timed alone on a 4096^3 problem
         'roofline_engine': {'kernel': 'tc::pipeline_kernel<GemmPolicy> (tcgen05 3xTF32 GEMM engine), 4096^3, isolated',
@@ -326,8 +438,14 @@ def run_b200(args):
                             'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops, burst)' if peaks else 'fallback 1590'},
         'algorithmic_flops_per_step': {'eigh_9n3': eig_flops, 'precondition_4ga(g+a)': prec_flops},
     }
+    if not args.no_parity:
+        # one more (untimed) step on a fresh batch, checked against the CPU oracle
+        x, y = devb[counter['i'] % NB]
+        opt.zero_grad(set_to_none=True)
+        crit(model(x), y).backward()
+        out['parity'] = parity_step(pre, model, world, rank, dev, hp)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline(args, steps=1, warmup=0, budget=120.0)
+        out['cpu_baseline'] = cpu_baseline(args, steps=2, warmup=1, budget=150.0)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -361,21 +479,43 @@ def usable_cores():
     return max(1, min(n, 32))
 
 
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref')
+
+
+def reference_kind():
+    """'reference' when the unmodified reference package was installed into oracle/_ref by
+    oracle/build_ref.sh (it travels to the GPU box with the snapshot), else 'port' (the oracle)."""
+    return 'reference' if os.path.isdir(os.path.join(REF_DIR, 'kfac')) else 'port'
+
+
 def cpu_reference_loop(args, steps, warmup, budget):
-    """The oracle port (same torch CPU ops as the reference) on the host cores."""
-    from oracle.kfac_oracle import OraclePreconditioner
+    """The reference's own CPU implementation of the path on the host cores: the UNMODIFIED
+    kfac.preconditioner.KFACPreconditioner from oracle/_ref (kind 'reference'), or -- when that install is
+    absent -- the oracle port (same torch CPU ops).  World size 1 (kfac/distributed.py:221-222)."""
     make_model, shape, classes, hp, wl = make_workload(args.model, args.batch)
     cores = usable_cores()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     model = make_model()
-    pre = OraclePreconditioner(model, factor_update_steps=1, inv_update_steps=1, **hp)
+    kind = reference_kind()
+    if kind == 'reference':
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        warnings.filterwarnings('ignore', message='NVIDIA Apex')
+        import logging
+        from kfac.preconditioner import KFACPreconditioner as RefPreconditioner
+        pre = RefPreconditioner(model, factor_update_steps=1, inv_update_steps=1, loglevel=logging.DEBUG, **hp)
+    else:
+        from oracle.kfac_oracle import OraclePreconditioner
+        pre = OraclePreconditioner(model, factor_update_steps=1, inv_update_steps=1, **hp)
     opt = torch.optim.SGD(model.parameters(), lr=hp['lr'], momentum=0.9)
     crit = torch.nn.CrossEntropyLoss()
-    x = torch.randn(*shape)
-    y = torch.randint(0, classes, (shape[0],))
+    NB = max(1, args.batches)
+    torch.manual_seed(1)
+    data = [(torch.randn(*shape), torch.randint(0, classes, (shape[0],))) for _ in range(NB)]
 
-    def one():
+    def one(i):
+        x, y = data[i % NB]
         opt.zero_grad(set_to_none=True)
         crit(model(x), y).backward()
         t0 = time.perf_counter()
@@ -389,18 +529,17 @@ def cpu_reference_loop(args, steps, warmup, budget):
     walls, kfacs = [], []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        k = one()
+        k = one(i)
         walls.append(time.perf_counter() - t0)
         kfacs.append(k)
         if time.perf_counter() - t_start + walls[-1] > budget:
             break
-    if len(walls) > warmup:
-        walls, kfacs = walls[warmup:], kfacs[warmup:]
-    else:
-        walls, kfacs = walls[-1:], kfacs[-1:]
+    warm_done = min(warmup, max(0, len(walls) - 1))
+    walls, kfacs = walls[warm_done:], kfacs[warm_done:]
     done, total, step_s = len(walls), sum(walls), sum(kfacs)
     return {'images_per_s': shape[0] * done / total, 'ms_per_step': total / done * 1e3,
-            'kfac_step_ms': step_s / done * 1e3, 'steps_done': done, 'cores': cores, 'workload': wl, 'batch': int(shape[0])}
+            'kfac_step_ms': step_s / done * 1e3, 'steps_done': done, 'warmup_done': warm_done, 'cores': cores,
+            'workload': wl, 'batch': int(shape[0]), 'kind': kind, 'distinct_batches': NB}
 
 
 def cpu_baseline(args, steps, warmup, budget):
@@ -408,7 +547,7 @@ def cpu_baseline(args, steps, warmup, budget):
     bench run always ends within minutes, whatever the host does."""
     import subprocess
     cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--model', args.model,
-           '--steps', str(steps), '--warmup', str(warmup), '--budget-s', str(budget)]
+           '--steps', str(steps), '--warmup', str(warmup), '--budget-s', str(budget), '--batches', str(args.batches)]
     if args.batch:
         cmd += ['--batch', str(args.batch)]
     env = dict(os.environ)
@@ -423,32 +562,32 @@ def cpu_baseline(args, steps, warmup, budget):
         cb['ms_per_step'] = d.get('ms_per_step')
         return cb
     except Exception as e:  # noqa: BLE001
-        return {'value': None, 'unit': 'images/s', 'cores': usable_cores(), 'kind': 'port',
-                'sample': f'CPU oracle did not finish one step within {budget + 90:.0f} s ({type(e).__name__})'}
-
-
-def _cpu_baseline_inline(args, steps, warmup, budget):
-    r = cpu_reference_loop(args, steps, warmup, budget)
-    return {'value': r['images_per_s'], 'unit': 'images/s', 'cores': r['cores'], 'kind': 'port',
-            'sample': f"{r['steps_done']} full step(s) of the same workload, no warm-up "
-                      f"(oracle port = the reference's torch CPU ops); kfac step() {r['kfac_step_ms']:.0f} ms",
-            'kfac_step_ms': r['kfac_step_ms'], 'ms_per_step': r['ms_per_step']}
+        return {'value': None, 'unit': 'images/s', 'cores': usable_cores(), 'kind': reference_kind(),
+                'sample': f'CPU arm did not finish one step within {budget + 90:.0f} s ({type(e).__name__})'}
 
 
 def run_reference(args):
+    """`--impl reference`: under torchrun only rank 0 works (the reference's single-process CPU path); the line
+    reports n_gpus = 1 and a world_size-1 global batch so that no N-GPU / 1-process ratio is formed from it."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    r = cpu_reference_loop(args, args.steps, min(args.warmup, 1), args.budget_s)
+    W = max(args.warmup, 1)
+    r = cpu_reference_loop(args, args.steps, W, args.budget_s)
+    kind = r['kind']
+    what = ('unmodified kfac.preconditioner.KFACPreconditioner (gpauloski/kfac-pytorch v0.4.2 installed into oracle/_ref)'
+            if kind == 'reference' else "oracle port (the reference's torch CPU ops)")
     out = {
         'impl': 'reference', 'metric': metric_name(args.model), 'value': r['images_per_s'], 'unit': 'images/s',
-        'n_gpus': args.gpus, 'steps': r['steps_done'], 'warmup': min(args.warmup, 1),
+        'n_gpus': 1, 'requested_gpus': args.gpus, 'steps': r['steps_done'], 'warmup': r['warmup_done'],
         'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': r['workload'], 'global_batch': r['batch'], 'parallelism': 'cpu, world_size 1'},
-        'cpu_baseline': {'value': r['images_per_s'], 'unit': 'images/s', 'cores': r['cores'], 'kind': 'port',
-                         'sample': f"{r['steps_done']} of {args.steps} requested steps within a "
-                                   f"{args.budget_s:.0f} s budget; kfac step() {r['kfac_step_ms']:.0f} ms"},
+        'dtype': 'f32 (model fwd/bwd fp32; K-FAC path fp32)', 'data': 'synthetic',
+        'config': {'workload': r['workload'], 'global_batch': r['batch'], 'grad_worker_fraction': 1.0,
+                   'parallelism': 'cpu, world_size 1 (one process on the host cores, at every requested N)',
+                   'distinct_batches': r['distinct_batches'], 'l2': 'n/a (host)'},
+        'cpu_baseline': {'value': r['images_per_s'], 'unit': 'images/s', 'cores': r['cores'], 'kind': kind,
+                         'sample': f"{r['steps_done']} of {args.steps} requested full steps (after {r['warmup_done']} warm-up) "
+                                   f"within a {args.budget_s:.0f} s budget, {what}; kfac step() {r['kfac_step_ms']:.0f} ms"},
         'e2e': {'value': r['images_per_s'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'kfac_step_ms': r['kfac_step_ms'],
     }

@@ -33,10 +33,11 @@ GOLDEN_NAMES = ['tiny_eigen', 'tiny_eigen_noprediv', 'tiny_inverse', 'tiny_sched
                 'conv_eigen', 'conv_inverse', 'conv_accum',
                 # widened cases: per-axis conv geometry, (batch, seq, feature) Linear inputs,
                 # callable hyper-parameters, skip_layers
-                'geom_eigen', 'geom_inverse', 'seq_eigen', 'tiny_callable', 'conv_skip']
+                'geom_eigen', 'geom_inverse', 'seq_eigen', 'tiny_callable', 'conv_skip',
+                # factors updated in step() with gradient accumulation; conv net on a factor/inverse schedule
+                'conv_nohook', 'conv_sched']
 
-# pinned against the oracle on the CPU; the GPU replay of these two is queued (not yet run on a B200)
-GOLDEN_CPU_ONLY = ['conv_nohook', 'conv_sched']
+GOLDEN_CPU_ONLY = []
 
 
 def model_for(name, fx=None):

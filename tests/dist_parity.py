@@ -84,13 +84,14 @@ def main():
                 print(f'world={world} method={method} symmetry_aware={sym} grad_worker_fraction={frac:.3f} '
                       f'collectives={pre._tdc.calls} worst rel-fro vs oracle = {t.item():.2e}', flush=True)
             ok = ok and t.item() < 1e-3
-    # wider layers (>= 64): the last precondition GEMM runs on the tcgen05 engine and its epilogue
-    # stores straight into the peers' arenas (fused compute + broadcast)
+    # wide layers (a = 833 / 769, g = 768): the large-matrix eigensolver class, an eigenbasis broadcast
+    # segment of several MB (C2) and a multi-tile (6 x 7 tiles of 128 x 128) tcgen05 precondition epilogue
+    # that stores straight into the peers' arenas (fused compute + broadcast, C3)
     class Wide(torch.nn.Module):
         def __init__(self):
             super().__init__()
-            self.l1 = torch.nn.Linear(96, 160)
-            self.l2 = torch.nn.Linear(160, 128)
+            self.l1 = torch.nn.Linear(832, 768)
+            self.l2 = torch.nn.Linear(768, 128)
             self.l3 = torch.nn.Linear(128, 5)
 
         def forward(self, x):
@@ -101,7 +102,7 @@ def main():
         ref_model = Wide()
         model = copy.deepcopy(ref_model).to(dev)
         torch.manual_seed(2)
-        gx = torch.randn(world * 16, 96)
+        gx = torch.randn(world * 16, 832)
         gy = torch.randint(0, 5, (world * 16,))
         x, y = gx[rank * 16:(rank + 1) * 16].to(dev), gy[rank * 16:(rank + 1) * 16].to(dev)
         pre = KFACPreconditioner(model, damping=0.003, grad_worker_fraction=frac)

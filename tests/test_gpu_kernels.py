@@ -228,8 +228,9 @@ def test_eigh_batched_sizes(lib, dev, kind):
 
 
 def test_eigh_tc_class(lib, dev):
-    # n >= 384 takes the tcgen05 Gram/apply kernels (two pairs per 128-row MMA tile)
-    mats = [make_psd(384, 'cov', 1), make_psd(500, 'lowrank', 2), make_psd(576, 'cluster', 3), make_psd(640, 'ident', 4)]
+    # mid sizes (384..640) and the first sizes of the large class (768, 800, 1000)
+    mats = [make_psd(384, 'cov', 1), make_psd(500, 'lowrank', 2), make_psd(576, 'cluster', 3), make_psd(640, 'ident', 4),
+            make_psd(768, 'cov', 7), make_psd(800, 'cluster', 8), make_psd(1000, 'lowrank', 9)]
     for F, Q, d, _ in run_eigh(lib, dev, mats):
         check_eigh(F, Q, d)
 
