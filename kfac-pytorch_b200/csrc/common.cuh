@@ -99,6 +99,7 @@ struct TcGemmArgs {
   int64_t a_kb_stride, b_kb_stride;
   int upper_only;                  // SYRK: compute tiles tn >= tm, mirror the rest
   int atomic;                      // epilogue accumulates with atomicAdd (split-K)
+  int accumulate;                  // D += alpha * A B^T with a plain read-modify-write (no split-K)
   int splits;                      // <= 0: automatic
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tc_pipeline.cuh"
 #include "eigh_common.cuh"
+#include "eigh_direct.cuh"
 
 #include <stdlib.h>
 
@@ -837,11 +838,28 @@ static size_t group_ws_bytes(const int* n, const std::vector<int>& idx) {
   return align_up(pl.total, 1024);
 }
 
-extern "C" size_t kfac_eigh_workspace_bytes(const int* n, int count) {
+// Which solver handles the factors with n > 128: the direct one (Householder tridiagonalisation + divide and
+// conquer + block-reflector back-transformation, eigh_direct.cu) or the round-1 block Jacobi of this file.
+static bool use_direct_solver() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KFAC_EIGH_SOLVER"); v = (e && e[0] == 'j') ? 0 : 1; }
+  return v != 0;
+}
+
+static size_t jacobi_workspace_bytes(const int* n, int count) {
   if (!n || count <= 0) return 0;
   std::vector<int> idx[2];
   split_groups(n, count, idx);
   return group_ws_bytes(n, idx[0]) + group_ws_bytes(n, idx[1]);
+}
+
+extern "C" size_t kfac_eigh_workspace_bytes(const int* n, int count) {
+  if (!n || count <= 0) return 0;
+  if (!use_direct_solver()) return jacobi_workspace_bytes(n, count);
+  std::vector<int> big, small;
+  for (int i = 0; i < count; ++i) (n[i] > 128 ? big : small).push_back(n[i]);
+  return align_up(eigh_direct_workspace_bytes(big.data(), (int)big.size()), 1024) +
+         jacobi_workspace_bytes(small.data(), (int)small.size());
 }
 
 static int eigh_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, int max_sweeps, float tol,
@@ -1119,6 +1137,42 @@ extern "C" int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* w
   for (int i = 0; i < count; ++i) {
     KFAC_CHECK_ARG(items[i].n > 0, "eigh item");
     ns[i] = items[i].n;
+  }
+  if (use_direct_solver()) {
+    // n > 128: direct solver on `s`; n <= 128: shared-memory Jacobi on a side stream (overlaps)
+    std::vector<kfac_eigh_item> big, small;
+    std::vector<int> nbig, nsmall;
+    for (int i = 0; i < count; ++i) {
+      if (items[i].n > 128) { big.push_back(items[i]); nbig.push_back(items[i].n); }
+      else { small.push_back(items[i]); nsmall.push_back(items[i].n); }
+    }
+    const size_t bd = align_up(eigh_direct_workspace_bytes(nbig.data(), (int)nbig.size()), 1024);
+    const size_t bs = jacobi_workspace_bytes(nsmall.data(), (int)nsmall.size());
+    if (!ws || ws_bytes < bd + bs) { set_error("eigh: workspace too small (%zu < %zu)", ws_bytes, bd + bs); return KFAC_ERR_WORKSPACE; }
+    static cudaStream_t sd = nullptr;
+    static cudaEvent_t ed_fork = nullptr, ed_join = nullptr;
+    cudaStream_t ss = s;
+    if (!big.empty() && !small.empty()) {
+      if (!sd) {
+        KFAC_CUDA(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+        KFAC_CUDA(cudaEventCreateWithFlags(&ed_fork, cudaEventDisableTiming));
+        KFAC_CUDA(cudaEventCreateWithFlags(&ed_join, cudaEventDisableTiming));
+      }
+      KFAC_CUDA(cudaEventRecord(ed_fork, s));
+      KFAC_CUDA(cudaStreamWaitEvent(sd, ed_fork, 0));
+      ss = sd;
+    }
+    if (!small.empty()) {
+      const int rc = eigh_run(small.data(), (int)small.size(), (char*)ws + bd, bs, max_sweeps, tol, ss, 0);
+      if (rc) return rc;
+    }
+    if (ss != s) KFAC_CUDA(cudaEventRecord(ed_join, ss));
+    if (!big.empty()) {
+      const int rc = eigh_direct_run(big.data(), (int)big.size(), ws, bd, s);
+      if (rc) return rc;
+    }
+    if (ss != s) KFAC_CUDA(cudaStreamWaitEvent(s, ed_join, 0));
+    return KFAC_OK;
   }
   std::vector<int> idx[2];
   split_groups(ns.data(), count, idx);

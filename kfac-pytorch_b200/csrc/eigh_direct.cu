@@ -1,0 +1,380 @@
+// Direct symmetric eigensolver for the large K-FAC factors (replaces torch.linalg.eigh of
+// kfac/layers/eigen.py:310,331 for n > 128):  F = H T H^T (sytrd.cu), T = Z L Z^T (stedc.cu),
+// Q = H Z by compact-WY block reflectors of 128 Householder vectors (this file; tcgen05 GEMMs).
+// Host side: workspace layout, the CTA-group schedule of the tridiagonalisation kernel, and the
+// enqueue of all stages on ONE stream without host synchronisation.
+#include "eigh_direct.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace kfac {
+
+namespace {
+
+constexpr int BT = 128;     // Householder vectors per block reflector of the back-transformation
+
+inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+struct BtBlock { float* S; float* Tm; const float* tau; int nb; };
+
+// S = V^T V of one block -> T (upper triangular, forward columnwise: H_0 H_1 ... = I - V T V^T)
+__global__ void __launch_bounds__(BT) larft_kernel(const BtBlock* blocks) {
+  extern __shared__ float larft_smem[];
+  float (*Ts)[BT + 1] = reinterpret_cast<float (*)[BT + 1]>(larft_smem);
+  const BtBlock b = blocks[blockIdx.x];
+  const int i = threadIdx.x, nb = b.nb;
+  for (int j = 0; j < BT; ++j) Ts[i][j] = 0.f;
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    const float tj = b.tau[j];
+    float acc = 0.f;
+    if (i < j) {
+      for (int l = i; l < j; ++l) acc = fmaf(Ts[i][l], b.S[l * BT + j], acc);
+      acc *= -tj;
+    }
+    __syncthreads();
+    if (i < j) Ts[i][j] = acc;
+    if (i == j) Ts[i][j] = tj;
+    __syncthreads();
+  }
+  for (int j = 0; j < BT; ++j) b.Tm[i * BT + j] = Ts[i][j];
+}
+
+// A (np x np, zero padded) <- F (n x n, ld n)
+__global__ void pad_copy_kernel(const float* F, int n, float* A, int np) {
+  const int64_t total = (int64_t)np * np;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / np), j = (int)(idx % np);
+    A[idx] = (i < n && j < n) ? F[(int64_t)i * n + j] : 0.f;
+  }
+}
+
+__global__ void transpose_ld_kernel(const float* src, int lds, float* dst, int ldd, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = by + r, j = bx + threadIdx.x;
+    tile[r][threadIdx.x] = (i < rows && j < cols) ? src[(int64_t)i * lds + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int j = bx + r, i = by + threadIdx.x;
+    if (j < cols && i < rows) dst[(int64_t)j * ldd + i] = tile[threadIdx.x][r];
+  }
+}
+
+// final outputs: QT_user / Q_user from ZT (rows = eigenvectors), eigenvalues clamped at 0 (eigen.py:321,344)
+__global__ void copy_rows_kernel(const float* src, int lds, float* dst, int ldd, int rows, int cols) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / cols), j = (int)(idx % cols);
+    dst[(int64_t)i * ldd + j] = src[(int64_t)i * lds + j];
+  }
+}
+__global__ void clamp_copy_kernel(const float* src, float* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = fmaxf(src[i], 0.f);
+}
+
+struct MatLayout {
+  int n, np, nblk, nbt;
+  size_t A, VT, Q0, Q1, Vp, Wp, part, col, tau, d, e, cpart, bar, fscr, iscr, S, Tm;
+};
+
+struct Layout {
+  std::vector<MatLayout> m;
+  size_t off_trd, off_jobs, off_dc, off_blocks, off_plan, plan_bytes, total;
+  int nblocks;
+};
+
+void make_layout(const int* n, int count, Layout& L) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.m.resize(count);
+  L.off_trd = take(sizeof(TrdMat) * count);
+  L.off_jobs = take(sizeof(TrdJob) * count);
+  L.off_dc = take(sizeof(DcMat) * count);
+  L.nblocks = 0;
+  for (int i = 0; i < count; ++i) L.nblocks += ceil_div(n[i], BT);
+  L.off_blocks = take(sizeof(BtBlock) * std::max(1, L.nblocks));
+  L.plan_bytes = stedc_plan_bytes(n, count);
+  L.off_plan = take(L.plan_bytes);
+  const int grid = sytrd_max_grid();
+  for (int i = 0; i < count; ++i) {
+    MatLayout& m = L.m[i];
+    m.n = n[i]; m.np = round_up(n[i], TRD_T); m.nblk = m.np / TRD_T; m.nbt = ceil_div(n[i], BT);
+    const size_t sq = (size_t)m.np * m.np * sizeof(float);
+    m.A = take(sq + (size_t)m.np * BT * 4); m.VT = take(sq); m.Q0 = take(sq); m.Q1 = take(sq);
+    m.Vp = take((size_t)m.np * TRD_NB * 4); m.Wp = take((size_t)m.np * TRD_NB * 4);
+    m.part = take((size_t)m.nblk * m.np * 4);
+    m.col = take((size_t)m.np * 4); m.tau = take((size_t)m.np * 4); m.d = take((size_t)m.np * 4); m.e = take((size_t)m.np * 4);
+    m.cpart = take((size_t)grid * TRD_CP * 4);
+    m.bar = take(256);
+    m.fscr = take((size_t)12 * m.n * 4); m.iscr = take((size_t)10 * m.n * 4);
+    m.S = take((size_t)m.nbt * BT * BT * 4); m.Tm = take((size_t)m.nbt * BT * BT * 4);
+  }
+  L.total = off;
+}
+
+// ---- CTA-group schedule of the tridiagonalisation kernel --------------------------------------
+// model of one matrix on C CTAs: n columns, each t0 (barriers + vector phases) + beta n^2 / C (tile products,
+// averaged over the shrinking trailing matrix)
+constexpr double T0 = 2.6e-6, BETA = 1.1e-11;
+double job_time(int n, int C) { return (double)n * (T0 + BETA * (double)n * n / C); }
+
+void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
+  // smallest makespan M such that the CTA-time of all jobs (each sized to finish within M) fits into G * M
+  auto ctas_for = [&](int ni, double M) {
+    const int cmax = std::max(1, std::min(G, (ni / TRD_T) * (ni / TRD_T + 1) / 2 / 2 + 1));   // >= 2 tiles per sub-group pays
+    for (int C = 1; C <= cmax; ++C) if (job_time(ni, C) <= M) return C;
+    return cmax;
+  };
+  double lo = 0, hi = 0;
+  for (int i = 0; i < count; ++i) { lo = std::max(lo, job_time(n[i], G)); hi += job_time(n[i], 1); }
+  hi = std::max(hi, lo);
+  for (int it = 0; it < 40; ++it) {
+    const double M = 0.5 * (lo + hi);
+    double area = 0;
+    for (int i = 0; i < count; ++i) { const int C = ctas_for(n[i], M); area += C * job_time(n[i], C); }
+    if (area <= 0.85 * G * M) hi = M; else lo = M;
+  }
+  std::vector<int> order(count), C(count);
+  for (int i = 0; i < count; ++i) { order[i] = i; C[i] = ctas_for(n[i], hi); }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return job_time(n[a], C[a]) > job_time(n[b], C[b]); });
+  std::vector<double> avail(G, 0.0);
+  struct Placed { double start; TrdJob job; };
+  std::vector<Placed> placed;
+  for (int i : order) {
+    int best = 0; double best_t = 1e300;
+    for (int c0 = 0; c0 + C[i] <= G; ++c0) {
+      double t = 0;
+      for (int c = c0; c < c0 + C[i]; ++c) t = std::max(t, avail[c]);
+      if (t < best_t) { best_t = t; best = c0; }
+    }
+    for (int c = best; c < best + C[i]; ++c) avail[c] = best_t + job_time(n[i], C[i]);
+    placed.push_back({best_t, TrdJob{i, best, C[i]}});
+  }
+  // a consistent global order (every CTA walks the list front to back) keeps the group barriers deadlock free
+  std::stable_sort(placed.begin(), placed.end(), [](const Placed& a, const Placed& b) { return a.start < b.start; });
+  jobs.clear();
+  for (auto& p : placed) jobs.push_back(p.job);
+}
+
+}  // namespace
+
+int gemm_tn_acc(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N, int K,
+                float alpha, cudaStream_t s) {
+  TcGemmArgs t{};
+  t.A = A; t.lda = lda; t.B = B; t.ldb = ldb; t.D = D; t.ldd = ldd; t.M = M; t.N = N; t.K = K;
+  t.kbatch = 1; t.alpha = alpha; t.splits = 1; t.accumulate = 1;
+  if (tc_gemm_supported(t)) return launch_tc_gemm(t, s);
+  GemmArgs g{};
+  g.A = A; g.sa_m = lda; g.sa_k = 1; g.B = B; g.sb_k = 1; g.sb_n = ldb;
+  g.C = D; g.ldc = ldd; g.M = M; g.N = N; g.K = K; g.batch = 1; g.splitk = 1; g.alpha = alpha; g.beta = 1.f;
+  return launch_gemm(g, s);
+}
+
+size_t eigh_direct_workspace_bytes(const int* n, int count) {
+  if (count <= 0) return 0;
+  Layout L;
+  make_layout(n, count, L);
+  return align_up(L.total, 1024);
+}
+
+// stage selector for tests / profiling: 1 = stop after the tridiagonalisation (d, e in the items' d / Q row 0),
+// 0 = full solve
+int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (count <= 0) return KFAC_OK;
+  std::vector<int> ns(count);
+  for (int i = 0; i < count; ++i) ns[i] = items[i].n;
+  Layout L;
+  make_layout(ns.data(), count, L);
+  if (!ws || ws_bytes < L.total) { set_error("eigh(direct): workspace too small (%zu < %zu)", ws_bytes, L.total); return KFAC_ERR_WORKSPACE; }
+  char* base = (char*)ws;
+  const int G = sytrd_max_grid();
+  std::vector<TrdMat> trd(count);
+  std::vector<DcMat> dc(count);
+  int np_max = 0;
+  for (int i = 0; i < count; ++i) {
+    const MatLayout& m = L.m[i];
+    TrdMat& t = trd[i];
+    t.A = (float*)(base + m.A); t.VT = (float*)(base + m.VT); t.tau = (float*)(base + m.tau);
+    t.d = (float*)(base + m.d); t.e = (float*)(base + m.e);
+    t.Vp = (float*)(base + m.Vp); t.Wp = (float*)(base + m.Wp); t.part = (float*)(base + m.part);
+    t.col = (float*)(base + m.col); t.cpart = (float*)(base + m.cpart); t.bar = (unsigned int*)(base + m.bar);
+    t.n = m.n; t.np = m.np; t.nblk = m.nblk; t.ldv = m.np;
+    np_max = std::max(np_max, m.np);
+    DcMat& d = dc[i];
+    d.d = t.d; d.e = t.e; d.Q[0] = (float*)(base + m.Q0); d.Q[1] = (float*)(base + m.Q1);
+    d.UT = t.A;                       // the working copy of F is dead after the tridiagonalisation
+    d.fscr = (float*)(base + m.fscr); d.iscr = (int*)(base + m.iscr);
+    d.n = m.n; d.ld = m.np; d.result_buf = 0;
+    // inputs / zeroed state
+    pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)m.np * m.np, 256)), 256, 0, s>>>(items[i].F, m.n, t.A, m.np);
+    KFAC_LAUNCH_CHECK();
+    KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)m.np * m.np * 4, s));
+    KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)m.np * TRD_NB * 4, s));
+    KFAC_CUDA(cudaMemsetAsync(t.Wp, 0, (size_t)m.np * TRD_NB * 4, s));
+    KFAC_CUDA(cudaMemsetAsync(t.bar, 0, 256, s));
+  }
+  std::vector<TrdJob> jobs;
+  make_schedule(ns.data(), count, G, jobs);
+  TrdMat* d_trd = (TrdMat*)(base + L.off_trd);
+  TrdJob* d_jobs = (TrdJob*)(base + L.off_jobs);
+  DcMat* d_dc = (DcMat*)(base + L.off_dc);
+  KFAC_CUDA(cudaMemcpyAsync(d_trd, trd.data(), sizeof(TrdMat) * count, cudaMemcpyHostToDevice, s));
+  KFAC_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(TrdJob) * jobs.size(), cudaMemcpyHostToDevice, s));
+  KFAC_CUDA(cudaMemcpyAsync(d_dc, dc.data(), sizeof(DcMat) * count, cudaMemcpyHostToDevice, s));
+  int rc;
+  if ((rc = launch_sytrd(d_trd, d_jobs, (int)jobs.size(), np_max, G, s))) return rc;
+  if ((rc = launch_stedc(dc.data(), d_dc, count, base + L.off_plan, L.plan_bytes, s))) return rc;
+
+  // ---- back-transformation: QT = Z^T B_{L-1}^T ... B_0^T, B_k = I - V_k T_k V_k^T
+  std::vector<BtBlock> blocks;
+  for (int i = 0; i < count; ++i) {
+    const MatLayout& m = L.m[i];
+    for (int kb = 0; kb < m.nbt; ++kb) {
+      const int j0 = kb * BT, nb = std::min(BT, m.n - j0);
+      blocks.push_back(BtBlock{(float*)(base + m.S) + (size_t)kb * BT * BT, (float*)(base + m.Tm) + (size_t)kb * BT * BT,
+                               trd[i].tau + j0, nb});
+    }
+  }
+  BtBlock* d_blocks = (BtBlock*)(base + L.off_blocks);
+  KFAC_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(BtBlock) * blocks.size(), cudaMemcpyHostToDevice, s));
+  for (int i = 0; i < count; ++i) {
+    const MatLayout& m = L.m[i];
+    const TrdMat& t = trd[i];
+    for (int kb = 0; kb < m.nbt; ++kb) {
+      const int j0 = kb * BT, nb = std::min(BT, m.n - j0);
+      float* S = (float*)(base + m.S) + (size_t)kb * BT * BT;
+      // S = V_k^T V_k over the rows >= j0 (the vectors are zero above)
+      if ((rc = gemm_tn_plain(t.VT + (size_t)j0 * t.ldv + j0, t.ldv, t.VT + (size_t)j0 * t.ldv + j0, t.ldv, S, BT, nb, nb,
+                              m.np - j0, s)))
+        return rc;
+    }
+  }
+  {
+    static bool attr = false;
+    const int lsmem = BT * (BT + 1) * (int)sizeof(float);
+    if (!attr) { KFAC_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lsmem)); attr = true; }
+    larft_kernel<<<(int)blocks.size(), BT, lsmem, s>>>(d_blocks);
+  }
+  KFAC_LAUNCH_CHECK();
+  for (int i = 0; i < count; ++i) {
+    const MatLayout& m = L.m[i];
+    const TrdMat& t = trd[i];
+    const DcMat& d = dc[i];
+    const int n = m.n, np = m.np;
+    float* Z = d.Q[d.result_buf];
+    float* ZT = d.Q[d.result_buf ^ 1];
+    transpose_ld_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32)), dim3(32, 8), 0, s>>>(Z, np, ZT, np, n, n);
+    KFAC_LAUNCH_CHECK();
+    float* VTt = t.A;          // nbt blocks of (np x BT): V_k T_k   (the UT workspace is dead after stedc)
+    float* Y = Z;              // np x BT scratch (Z is dead after the transpose)
+    for (int kb = 0; kb < m.nbt; ++kb) {
+      const int j0 = kb * BT, nb = std::min(BT, n - j0);
+      GemmArgs g{};            // VTt_k[r][i'] = sum_i VT[j0 + i][r] T_k[i][i']   (fp32 SIMT, strided A)
+      g.A = t.VT + (size_t)j0 * t.ldv + j0; g.sa_m = 1; g.sa_k = t.ldv;
+      g.B = (float*)(base + m.Tm) + (size_t)kb * BT * BT; g.sb_k = BT; g.sb_n = 1;
+      g.C = VTt + (size_t)kb * np * BT + (size_t)j0 * BT; g.ldc = BT;
+      g.M = np - j0; g.N = BT; g.K = nb; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.beta = 0.f;
+      if ((rc = launch_gemm(g, s))) return rc;
+    }
+    for (int kb = m.nbt - 1; kb >= 0; --kb) {
+      const int j0 = kb * BT, nbp = std::min(BT, np - j0);
+      // Y = ZT[:, j0:] V_k[j0:, :]   (n x nbp)
+      if ((rc = gemm_tn_plain(ZT + j0, np, t.VT + (size_t)j0 * t.ldv + j0, t.ldv, Y, BT, n, nbp, np - j0, s))) return rc;
+      // ZT[:, j0:] -= Y (V_k T_k)[j0:, :]^T
+      if ((rc = gemm_tn_acc(Y, BT, VTt + (size_t)kb * np * BT + (size_t)j0 * BT, BT, ZT + j0, np, n, np - j0, nbp, -1.f, s)))
+        return rc;
+    }
+    const int ldq = items[i].ldq > 0 ? items[i].ldq : n;
+    if (items[i].QT) {
+      copy_rows_kernel<<<std::min(2048, ceil_div((int64_t)n * n, 256)), 256, 0, s>>>(ZT, np, items[i].QT, ldq, n, n);
+      KFAC_LAUNCH_CHECK();
+    }
+    transpose_ld_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32)), dim3(32, 8), 0, s>>>(ZT, np, items[i].Q, ldq, n, n);
+    KFAC_LAUNCH_CHECK();
+    clamp_copy_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d.d, items[i].d, n);
+    KFAC_LAUNCH_CHECK();
+  }
+  return KFAC_OK;
+}
+
+}  // namespace kfac
+
+// test / profiling entry (not in the public header): tridiagonalisation only
+extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e, float* VT, int ldv, float* tau,
+                                       void* ws, size_t ws_bytes, int ncta, void* stream) {
+  using namespace kfac;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int np = round_up(n, TRD_T), nblk = np / TRD_T;
+  const int G = sytrd_max_grid();
+  if (ncta <= 0 || ncta > G) ncta = G;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t oA = take((size_t)np * (np + 128) * 4), oVT = take((size_t)np * np * 4), oVp = take((size_t)np * TRD_NB * 4),
+               oWp = take((size_t)np * TRD_NB * 4), oPart = take((size_t)nblk * np * 4), oCol = take((size_t)np * 4),
+               oTau = take((size_t)np * 4), oD = take((size_t)np * 4), oE = take((size_t)np * 4),
+               oC = take((size_t)G * TRD_CP * 4), oBar = take(256), oMat = take(sizeof(TrdMat)), oJob = take(sizeof(TrdJob));
+  if (!ws || ws_bytes < off) { set_error("sytrd test: workspace too small (%zu < %zu)", ws_bytes, off); return KFAC_ERR_WORKSPACE; }
+  char* base = (char*)ws;
+  TrdMat t;
+  t.A = (float*)(base + oA); t.VT = (float*)(base + oVT); t.tau = (float*)(base + oTau); t.d = (float*)(base + oD);
+  t.e = (float*)(base + oE); t.Vp = (float*)(base + oVp); t.Wp = (float*)(base + oWp); t.part = (float*)(base + oPart);
+  t.col = (float*)(base + oCol); t.cpart = (float*)(base + oC); t.bar = (unsigned int*)(base + oBar);
+  t.n = n; t.np = np; t.nblk = nblk; t.ldv = np;
+  pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)np * np, 256)), 256, 0, s>>>(F, n, t.A, np);
+  KFAC_LAUNCH_CHECK();
+  KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)np * np * 4, s));
+  KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)np * TRD_NB * 4, s));
+  KFAC_CUDA(cudaMemsetAsync(t.Wp, 0, (size_t)np * TRD_NB * 4, s));
+  KFAC_CUDA(cudaMemsetAsync(t.bar, 0, 256, s));
+  TrdJob job{0, 0, ncta};
+  KFAC_CUDA(cudaMemcpyAsync(base + oMat, &t, sizeof(t), cudaMemcpyHostToDevice, s));
+  KFAC_CUDA(cudaMemcpyAsync(base + oJob, &job, sizeof(job), cudaMemcpyHostToDevice, s));
+  int rc;
+  if ((rc = launch_sytrd((TrdMat*)(base + oMat), (TrdJob*)(base + oJob), 1, np, G, s))) return rc;
+  KFAC_CUDA(cudaMemcpyAsync(d, t.d, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  KFAC_CUDA(cudaMemcpyAsync(e, t.e, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  KFAC_CUDA(cudaMemcpyAsync(tau, t.tau, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  if (VT) KFAC_CUDA(cudaMemcpy2DAsync(VT, (size_t)ldv * 4, t.VT, (size_t)np * 4, (size_t)n * 4, n, cudaMemcpyDeviceToDevice, s));
+  return KFAC_OK;
+}
+
+// test entry: D&C on a given tridiagonal (d, e) -> eigenvalues (ascending) and eigenvectors (columns of Q, ld n)
+extern "C" int kfac_experimental_stedc(const float* d_in, const float* e_in, int n, float* evals, float* Q, void* ws,
+                                       size_t ws_bytes, void* stream) {
+  using namespace kfac;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int np = round_up(n, TRD_T);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t oQ0 = take((size_t)np * np * 4), oQ1 = take((size_t)np * np * 4), oUT = take((size_t)np * np * 4),
+               oD = take((size_t)np * 4), oE = take((size_t)np * 4), oF = take((size_t)12 * n * 4), oI = take((size_t)10 * n * 4),
+               oMat = take(sizeof(DcMat));
+  const size_t pb = stedc_plan_bytes(&n, 1);
+  const size_t oPlan = take(pb);
+  if (!ws || ws_bytes < off) { set_error("stedc test: workspace too small (%zu < %zu)", ws_bytes, off); return KFAC_ERR_WORKSPACE; }
+  char* base = (char*)ws;
+  DcMat m;
+  m.d = (float*)(base + oD); m.e = (float*)(base + oE); m.Q[0] = (float*)(base + oQ0); m.Q[1] = (float*)(base + oQ1);
+  m.UT = (float*)(base + oUT); m.fscr = (float*)(base + oF); m.iscr = (int*)(base + oI); m.n = n; m.ld = np; m.result_buf = 0;
+  KFAC_CUDA(cudaMemcpyAsync(m.d, d_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  KFAC_CUDA(cudaMemsetAsync(m.e, 0, (size_t)np * 4, s));
+  if (n > 1) KFAC_CUDA(cudaMemcpyAsync(m.e, e_in, (size_t)(n - 1) * 4, cudaMemcpyDeviceToDevice, s));
+  KFAC_CUDA(cudaMemcpyAsync(base + oMat, &m, sizeof(m), cudaMemcpyHostToDevice, s));
+  int rc;
+  if ((rc = launch_stedc(&m, (DcMat*)(base + oMat), 1, base + oPlan, pb, s))) return rc;
+  KFAC_CUDA(cudaMemcpyAsync(evals, m.d, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  KFAC_CUDA(cudaMemcpy2DAsync(Q, (size_t)n * 4, m.Q[m.result_buf], (size_t)np * 4, (size_t)n * 4, n, cudaMemcpyDeviceToDevice, s));
+  return KFAC_OK;
+}
+
+extern "C" size_t kfac_experimental_direct_workspace_bytes(int n) {
+  const int np = (n + 63) / 64 * 64;
+  return (size_t)np * np * 4 * 4 + (size_t)np * 4096 + (1u << 22);
+}

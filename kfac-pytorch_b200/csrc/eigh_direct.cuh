@@ -1,0 +1,70 @@
+// Direct (non-iterative) symmetric eigensolver for the large factors (n > 128):
+//   1. sytrd.cu   Householder tridiagonalisation  F = H T H^T   (persistent multi-CTA kernel, fp32 SIMT,
+//                 lower-triangle 64x64 tiles resident in L2, two group barriers per column)
+//   2. stedc.cu   divide and conquer on T (Cuppen / Gu-Eisenstat): leaf solves in shared memory,
+//                 rank-one merges = deflation + secular equation + one tcgen05 GEMM per merge
+//   3. eigh_direct.cu  back-transformation Q = H Z with compact-WY block reflectors (tcgen05 GEMMs)
+// Replaces torch.linalg.eigh of kfac/layers/eigen.py:310,331 (LAPACK ssyevd = the same three stages).
+#pragma once
+#include "common.cuh"
+
+namespace kfac {
+
+constexpr int TRD_NB = 32;        // panel width (columns per block reflector of the reduction)
+constexpr int TRD_T = 64;         // tile edge of the lower-triangle tiling
+constexpr int TRD_THREADS = 1024; // 4 sub-groups of 8 warps
+constexpr int TRD_CP = 72;        // floats of per-CTA partial scalars: [0,32) W^T v, [32,64) V^T v, 64 v^T A v, 65 |x|^2
+
+struct TrdMat {
+  float* A;        // np x np working copy of F (zero padded); only tiles I >= J are kept up to date
+  float* VT;       // n x ldv: row j = Householder vector v_j (v_j[j+1] = 1, zero for r <= j)
+  float* tau;      // n
+  float* d;        // n     diagonal of T
+  float* e;        // n     sub-diagonal of T (e[j] couples j, j+1)
+  float* Vp;       // np x TRD_NB panel of Householder vectors
+  float* Wp;       // np x TRD_NB panel of w vectors
+  float* part;     // nblk x np partial products of the symmetric matrix-vector product
+  float* col;      // np  effective next column
+  float* cpart;    // ncta x TRD_CP per-CTA partial scalars
+  unsigned int* bar;  // group barrier counter (zeroed before launch)
+  int n, np, nblk, ldv;
+};
+
+struct TrdJob { int mat, cta0, ncta; };
+
+// all jobs of one launch; a CTA processes the jobs that contain it in list order
+int launch_sytrd(const TrdMat* d_mats, const TrdJob* d_jobs, int njobs, int np_max, int grid, cudaStream_t s);
+int sytrd_max_grid();
+
+// ---- divide and conquer (stedc.cu)
+struct DcMat {
+  float* d;        // n   in: diagonal of T, out: eigenvalues (ascending)
+  float* e;        // n   sub-diagonal (destroyed)
+  float* Q[2];     // n x ld ping-pong eigenvector matrices (columns = eigenvectors); result in Q[result_buf]
+  float* UT;       // n x ld workspace (rows = coefficient vectors of the merged eigenvectors)
+  float* fscr;     // 10 n floats of scratch
+  int* iscr;       // 8 n ints of scratch
+  int n, ld;
+  int result_buf;
+};
+
+struct DcPlanHost;   // opaque (stedc.cu)
+// workspace bytes for the plan tables (merge lists, leaf descriptors) of a batch
+size_t stedc_plan_bytes(const int* n, int count);
+// eigen-decomposition of `count` tridiagonal matrices; d_mats/h_mats describe them (device pointers inside);
+// plan_ws: device scratch of stedc_plan_bytes(); all work is enqueued on `s`
+int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, cudaStream_t s);
+
+// leaf solver exported by eigh.cu (shared-memory Jacobi on dense <= 64 x 64 problems, direct mode)
+struct EighMat;
+int launch_jacobi_direct64(EighMat* d_mats, const int* d_list, int count, cudaStream_t s);
+
+// plain fp32 TN GEMM on the tcgen05 engine: D = alpha * A B^T (+ D when accumulate)
+int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
+                  int K, cudaStream_t s);
+size_t eigh_direct_workspace_bytes(const int* n, int count);
+int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, cudaStream_t s);
+int gemm_tn_acc(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
+                int K, float alpha, cudaStream_t s);
+
+}  // namespace kfac

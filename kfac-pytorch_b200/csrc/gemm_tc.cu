@@ -21,7 +21,7 @@ struct TcParams {
   CUtensorMap tmA, tmB;
   float* D; int64_t ldd;
   int M, N, K, kbatch;
-  int tiles_m, tiles_n, splits, upper_only, atomic;
+  int tiles_m, tiles_n, splits, upper_only, atomic, accum;
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
   float* peerD[7]; int npeer;
@@ -75,6 +75,13 @@ struct GemmPolicy {
       v[j] = x;
     }
     if (!p.atomic && !mirror && (p.ldd & 3) == 0 && nb + 32 <= p.N) {
+      if (p.accum) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 o = *reinterpret_cast<const float4*>(drow + j);
+          v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -94,7 +101,7 @@ struct GemmPolicy {
           atomicAdd(drow + j, v[j]);
           if (mirror) atomicAdd(p.D + (int64_t)(nb + j) * p.ldd + m, v[j]);
         } else {
-          drow[j] = v[j];
+          drow[j] = p.accum ? drow[j] + v[j] : v[j];
           if (mirror) p.D[(int64_t)(nb + j) * p.ldd + m] = v[j];
           for (int q = 0; q < p.npeer; ++q) p.peerD[q][(int64_t)m * p.ldd + nb + j] = v[j];
         }
@@ -190,7 +197,8 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream) {
   if ((rc = make_tmap(&p.tmB, a.B, a.N, a.K, a.ldb, kbatch, a.b_kb_stride))) return rc;
   p.D = a.D; p.ldd = a.ldd; p.M = a.M; p.N = a.N; p.K = a.K; p.kbatch = kbatch;
   p.tiles_m = ceil_div(a.M, TBM); p.tiles_n = ceil_div(a.N, TBN);
-  p.upper_only = a.upper_only; p.atomic = a.atomic; p.alpha = a.alpha;
+  p.upper_only = a.upper_only; p.atomic = a.atomic; p.alpha = a.alpha; p.accum = a.accumulate;
+  if (a.accumulate && (a.atomic || a.upper_only || a.npeer > 0 || a.splits > 1)) { set_error("tc_gemm: accumulate needs the plain single-split epilogue"); return KFAC_ERR_BAD_ARG; }
   p.epi = a.epi; p.E = a.E; p.lde = a.lde; p.dg = a.dg; p.da = a.da; p.damping = a.damping;
   p.npeer = a.npeer;
   for (int q = 0; q < a.npeer && q < 7; ++q) p.peerD[q] = a.peerD[q];
