@@ -182,12 +182,16 @@ typedef struct kfac_grad_item {
   int g, a;
   int ldp; /* leading dimension of P */
 } kfac_grad_item;
-/* scratch: device double[1] (vg) ; scale_out: device float[1] (nu) */
+/* Both calls run as ONE launch over all layers and are bitwise reproducible (fixed assignment of elements
+ * to threads, fixed-order reduction; no floating-point atomics): every data-parallel replica that
+ * preconditions locally gets the same nu.  ws: device workspace of kfac_grad_workspace_bytes(count) bytes
+ * (item table + partial sums); scale_out: device float[1] (nu). */
+size_t kfac_grad_workspace_bytes(int count);
 int kfac_grad_scale(const kfac_grad_item* items, int count, float kl_clip,
-                    float lr, double* scratch, float* scale_out, void* stream);
+                    float lr, void* ws, size_t ws_bytes, float* scale_out, void* stream);
 /* scale may be NULL (no clipping: scale = 1) */
 int kfac_grad_update(const kfac_grad_item* items, int count, const float* scale,
-                     void* stream);
+                     void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------- peer memory
  * Buffers that other ranks of the node write into directly (CUDA IPC over NVLink).

@@ -67,8 +67,9 @@ SIGNATURES = {
     'kfac_transpose': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     'kfac_precondition_workspace_bytes': (c_size_t, [C.POINTER(PrecondItem), c_int]),
     'kfac_precondition': (c_int, [C.POINTER(PrecondItem), c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]),
-    'kfac_grad_scale': (c_int, [C.POINTER(GradItem), c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
-    'kfac_grad_update': (c_int, [C.POINTER(GradItem), c_int, c_void_p, c_void_p]),
+    'kfac_grad_workspace_bytes': (c_size_t, [c_int]),
+    'kfac_grad_scale': (c_int, [C.POINTER(GradItem), c_int, c_float, c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
+    'kfac_grad_update': (c_int, [C.POINTER(GradItem), c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'kfac_peer_alloc': (c_int, [c_size_t, C.POINTER(c_void_p), c_void_p]),
     'kfac_peer_open': (c_int, [c_void_p, C.POINTER(c_void_p)]),
     'kfac_peer_close': (c_int, [c_void_p]),

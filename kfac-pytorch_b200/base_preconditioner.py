@@ -29,7 +29,7 @@ from kfac_b200 import _cabi
 from kfac_b200.assignment import WorkAssignment
 from kfac_b200.distributed import ArenaCommunicator, get_rank
 from kfac_b200.enums import ComputeMethod
-from kfac_b200.layers import KFACLayer
+from kfac_b200.layers import KFACLayer, cast_for_factor
 
 logger = logging.getLogger(__name__)
 
@@ -133,6 +133,17 @@ def build_comm_plan(layers: list[tuple[str, KFACLayer]], assignment: WorkAssignm
     return inv_segments, grad_segments
 
 
+def _release_peer_memory(peer_bases: list[int], own_ptr: int) -> None:
+    """Finalizer of the fused-broadcast arena: unmap the peers' arenas, free our own."""
+    try:
+        lib = _cabi.load()
+        for b in peer_bases:
+            lib.kfac_peer_close(C.c_void_p(b))
+        lib.kfac_peer_free(C.c_void_p(own_ptr))
+    except Exception:  # noqa: BLE001  (interpreter shutdown)
+        pass
+
+
 class BaseKFACPreconditioner:
     """K-FAC distributed gradient preconditioner (native sm_100a hot path)."""
 
@@ -196,6 +207,7 @@ class BaseKFACPreconditioner:
         self._scratch_bwd = _Scratch()      # transposes (backward hooks, autograd thread)
         self._eig_scratch = _Scratch()      # eigensolver workspace
         self._gemm_scratch = _Scratch()     # precondition / inverse temporaries
+        self._grad_scratch = _Scratch()     # kl-clip / write-back item table + partial sums
         self._factors_dirty = False
         self._pending_alpha: dict[float, list[tuple[KFACLayer, str]]] = {}
         self.last_grad_scale: torch.Tensor | None = None   # device scalar nu of the last step
@@ -329,48 +341,89 @@ class BaseKFACPreconditioner:
         """P arena.  With gradient broadcasts (KAISA HYBRID/MEM-OPT) it is allocated as CUDA-IPC
         peer memory and mapped into the other ranks of the gradient-receiver group, so the last
         precondition GEMM can store its tiles straight into every receiver (fused compute +
-        broadcast over NVLink) instead of a broadcast per source afterwards."""
+        broadcast over NVLink) instead of a broadcast per source afterwards.
+
+        Every rank of the group takes the same sequence of collectives whatever happens locally:
+        the local attempts (allocation, opening the peers' handles) are wrapped individually and the
+        group agrees on the outcome with a MIN all-reduce of a success flag after each of them; the
+        fused path is enabled only if EVERY rank succeeded, otherwise all ranks release what they hold
+        and fall back to NCCL broadcasts together."""
         import torch.distributed as dist
         want = (self.fused_grad_broadcast and dist.is_available() and dist.is_initialized()
                 and self._assignment.broadcast_gradients() and self._layers)
+        group = None
         if want:
-            try:
-                name0 = next(iter(self._layers.values()))[0]
-                group = self._assignment.grad_receiver_group(name0)
-                if dist.get_backend(group) != 'nccl' or dist.get_world_size(group) < 2 \
-                        or dist.get_world_size(group) > 8:
-                    raise RuntimeError('fused broadcast needs an NCCL group of 2..8 ranks')
-                lib = _cabi.load()
-                ptr = C.c_void_p()
-                handle = (C.c_ubyte * 64)()
-                _cabi.check(lib.kfac_peer_alloc(numel * 4, C.byref(ptr), handle), 'kfac_peer_alloc')
+            name0 = next(iter(self._layers.values()))[0]
+            group = self._assignment.grad_receiver_group(name0)
+            # pure functions of (group, backend): identical on every rank, no collective involved
+            want = (dist.get_backend(group) == 'nccl' and 2 <= dist.get_world_size(group) <= 8)
+        if not want:
+            return torch.zeros(numel, dtype=torch.float32, device=device)
 
-                class _Raw:   # zero-copy torch view of the cudaMalloc'ed buffer
-                    pass
-                raw = _Raw()
-                raw.__cuda_array_interface__ = {'shape': (numel,), 'typestr': '<f4', 'data': (ptr.value, False),
-                                                'version': 3, 'strides': None}
-                arena = torch.as_tensor(raw, device=device)
-                me = get_rank()
-                gathered = [None] * dist.get_world_size(group)
-                dist.all_gather_object(gathered, (me, bytes(handle)), group=group)
-                bases = {}
-                for r, h in gathered:
-                    if r == me:
-                        continue
-                    out = C.c_void_p()
-                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
-                    _cabi.check(lib.kfac_peer_open(buf, C.byref(out)), 'kfac_peer_open')
-                    bases[r] = out.value
-                self._peer_p_bases = bases
-                self._p_raw = raw
-                self._row_group = group
-                self._row_token = torch.zeros(1, dtype=torch.float32, device=device)
-                return arena
-            except Exception as e:  # noqa: BLE001
-                logger.warning('fused gradient broadcast unavailable (%s); using NCCL broadcasts', e)
-                self._peer_p_bases = None
-        return torch.zeros(numel, dtype=torch.float32, device=device)
+        def agree(ok: bool) -> bool:
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return bool(flag.item())
+
+        lib = _cabi.load()
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        why = ''
+        try:
+            _cabi.check(lib.kfac_peer_alloc(numel * 4, C.byref(ptr), handle), 'kfac_peer_alloc')
+            ok = True
+        except Exception as e:  # noqa: BLE001
+            ok, why = False, str(e)
+        if not agree(ok):
+            if ok:
+                lib.kfac_peer_free(ptr)
+            logger.warning('fused gradient broadcast unavailable (%s); using NCCL broadcasts', why or 'a peer failed')
+            return torch.zeros(numel, dtype=torch.float32, device=device)
+        me = get_rank()
+        gathered = [None] * dist.get_world_size(group)
+        dist.all_gather_object(gathered, (me, bytes(handle)), group=group)
+        bases: dict[int, int] = {}
+        try:
+            for r, h in gathered:
+                if r == me:
+                    continue
+                out = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                _cabi.check(lib.kfac_peer_open(buf, C.byref(out)), 'kfac_peer_open')
+                bases[r] = out.value
+            ok = True
+        except Exception as e:  # noqa: BLE001
+            ok, why = False, str(e)
+        if not agree(ok):
+            for b in bases.values():
+                lib.kfac_peer_close(C.c_void_p(b))
+            dist.barrier(group=group)       # nobody frees an allocation a peer may still have mapped
+            lib.kfac_peer_free(ptr)
+            logger.warning('fused gradient broadcast unavailable (%s); using NCCL broadcasts', why or 'a peer failed')
+            return torch.zeros(numel, dtype=torch.float32, device=device)
+
+        class _Raw:   # zero-copy torch view of the cudaMalloc'ed buffer
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {'shape': (numel,), 'typestr': '<f4', 'data': (ptr.value, False),
+                                        'version': 3, 'strides': None}
+        arena = torch.as_tensor(raw, device=device)
+        self._peer_p_bases = bases
+        self._p_raw = raw
+        self._p_ptr = ptr.value
+        self._row_group = group
+        self._row_token = torch.zeros(1, dtype=torch.float32, device=device)
+        import weakref
+        self._peer_finalizer = weakref.finalize(self, _release_peer_memory, list(bases.values()), ptr.value)
+        return arena
+
+    def close(self) -> None:
+        """Release the CUDA-IPC mappings and the peer-visible P arena (also runs when the
+        preconditioner is garbage collected)."""
+        fin = getattr(self, '_peer_finalizer', None)
+        if fin is not None and fin.alive:
+            fin()
+        self._peer_p_bases = None
 
     # ------------------------------------------------------------ state dict
     def state_dict(self, include_factors: bool = True) -> dict[str, Any]:
@@ -380,7 +433,12 @@ class BaseKFACPreconditioner:
             if not callable(v):
                 sd[key] = v
         if include_factors:
-            self._flush_factor_updates()
+            # the reference's factors are already EMA-updated and all-reduced when a state dict is taken
+            # (both happen in the hooks, base_preconditioner.py:452-457): flush + reduce, and hand out
+            # snapshots (the arena views keep changing in place)
+            if self._arenas_ready:
+                self._flush_factor_updates()
+                self._reduce_factors()
             sd['layers'] = {name: layer.state_dict() for name, layer in self._layers.values()}
         return sd
 
@@ -420,7 +478,7 @@ class BaseKFACPreconditioner:
         self._ensure_arenas(x.device)
         if layer._a_pending:       # a completed accumulation window is still queued
             self._flush_factor_updates()
-        layer.module.accumulate_a(x, layer._a_batch_view, self._scratch)
+        layer.module.accumulate_a(cast_for_factor(x, layer.factor_dtype), layer._a_batch_view, self._scratch)
         layer._a_count += 1
         self._mini_steps[name] += 1
         if self._update_factors_in_hook and self._mini_steps[name] % self._accumulation_steps == 0:
@@ -439,7 +497,8 @@ class BaseKFACPreconditioner:
         if layer._g_pending:
             self._flush_factor_updates()
         # the backward hook runs on the autograd thread: it gets its own scratch buffer
-        layer.module.accumulate_g(g, layer._g_batch_view, self._grad_scale_value(layer), self._scratch_bwd)
+        layer.module.accumulate_g(cast_for_factor(g, layer.factor_dtype), layer._g_batch_view,
+                                  self._grad_scale_value(layer), self._scratch_bwd)
         layer._g_count += 1
         if self._update_factors_in_hook and self._mini_steps[name] % self._accumulation_steps == 0:
             self._mark_pending(layer, 'g')
@@ -700,13 +759,15 @@ class BaseKFACPreconditioner:
         stream = _cabi.stream_ptr()
         kl_clip = self.kl_clip
         scale_ptr = None
+        need = lib.kfac_grad_workspace_bytes(len(ll))
+        ws = self._grad_scratch.get(need, self._device)
         if kl_clip is not None and ll:
-            _cabi.check(lib.kfac_grad_scale(items, len(ll), float(kl_clip), float(self.lr),
-                                            self._vg.data_ptr(), self._nu.data_ptr(), stream), 'kfac_grad_scale')
+            _cabi.check(lib.kfac_grad_scale(items, len(ll), float(kl_clip), float(self.lr), ws.data_ptr(), need,
+                                            self._nu.data_ptr(), stream), 'kfac_grad_scale')
             scale_ptr = self._nu.data_ptr()
             self.last_grad_scale = self._nu
         if ll:
-            _cabi.check(lib.kfac_grad_update(items, len(ll), scale_ptr, stream), 'kfac_grad_update')
+            _cabi.check(lib.kfac_grad_update(items, len(ll), scale_ptr, ws.data_ptr(), need, stream), 'kfac_grad_update')
         for _, layer in ll:
             layer._grad_ready = False
 

@@ -6,12 +6,14 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --use_fast_math=false"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 OBJS=""
-for f in api gemm_simt gemm_tc factor eigh sytrd stedc eigh_direct precond jacobi_systolic factor_ema_tiled $EXTRA_SRCS; do
+for f in api gemm_simt gemm_tc factor eigh sytrd stedc eigh_direct precond jacobi_systolic $EXTRA_SRCS; do
   if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ common.cuh -nt $f.o ] || [ tc_common.cuh -nt $f.o ] || [ tc_pipeline.cuh -nt $f.o ] || { [ $f = jacobi_systolic ] && [ jacobi_systolic.cuh -nt $f.o ]; } || { { [ $f = jacobi_systolic ] || [ $f = eigh ]; } && [ eigh_common.cuh -nt $f.o ]; } || [ ../../include/kfac_b200.h -nt $f.o ] || [ eigh_direct.cuh -nt $f.o ]; then
     echo "nvcc $f.cu"
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o $f.o
   fi
   OBJS="$OBJS $f.o"
 done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libkfac_b200.so $OBJS -lcudart_static -ldl -lrt -lpthread
+# link to a temporary name and rename: a gpurun snapshot never sees a half-written library
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libkfac_b200.so.tmp $OBJS -lcudart_static -ldl -lrt -lpthread
+mv -f libkfac_b200.so.tmp libkfac_b200.so
 echo "built $(pwd)/libkfac_b200.so"

@@ -100,6 +100,7 @@ struct TcGemmArgs {
   int upper_only;                  // SYRK: compute tiles tn >= tm, mirror the rest
   int atomic;                      // epilogue accumulates with atomicAdd (split-K)
   int accumulate;                  // D += alpha * A B^T with a plain read-modify-write (no split-K)
+  float* slab; int64_t slab_stride; // deterministic split-K: split sp stores its partial tile to slab + sp * slab_stride (ld = ldd)
   int splits;                      // <= 0: automatic
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;

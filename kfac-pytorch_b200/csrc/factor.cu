@@ -187,26 +187,59 @@ __global__ void to_feature_major_kernel(const void* xin, int64_t rows, int feat,
 }
 
 // ------------------------------------------------------------------ EMA
-struct EmaBatch { kfac_ema_item it[48]; int count; float alpha; };
-__global__ void ema_kernel(EmaBatch eb) {
-  const kfac_ema_item it = eb.it[blockIdx.y];
-  const int d = it.d;
-  const int64_t total = (int64_t)d * d;
+// factor = alpha * (first ? I : factor) + (1 - alpha) * inv_count * (batch + batch^T) / 2, batch = 0.
+// A CTA owns the pair of 32 x 32 tiles (ti, tj) / (tj, ti): both are read and written row-wise, the
+// transposition happens in shared memory (every access is coalesced: 5 x 4 d^2 bytes at HBM speed).
+struct EmaBatch {
+  kfac_ema_item it[40];
+  int first_block[41];   // prefix sums of the number of tile pairs T (T + 1) / 2 per item
+  int count;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(256) ema_kernel(const __grid_constant__ EmaBatch eb) {
+  __shared__ float A[32][33], B[32][33];
+  int item = 0;
+  while (item + 1 < eb.count && (int)blockIdx.x >= eb.first_block[item + 1]) ++item;
+  const kfac_ema_item it = eb.it[item];
+  const int p = blockIdx.x - eb.first_block[item];
+  // unrank the tile pair (ti <= tj) from p = tj (tj + 1) / 2 + ti
+  int tj = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+  while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
+  while (tj * (tj + 1) / 2 > p) --tj;
+  const int ti = p - tj * (tj + 1) / 2;
+  const int d = it.d, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float alpha = eb.alpha, beta = (1.f - eb.alpha) * it.inv_count * 0.5f;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(idx / d), j = (int)(idx % d);
-    if (j < i) continue;
-    const float bij = it.batch[idx], bji = it.batch[(int64_t)j * d + i];
-    const float s = beta * (bij + bji);
-    const float fij = it.first ? (i == j ? 1.f : 0.f) : it.factor[idx];
-    it.factor[idx] = alpha * fij + s;
-    it.batch[idx] = 0.f;
-    if (j != i) {
-      const int64_t t = (int64_t)j * d + i;
-      const float fji = it.first ? 0.f : it.factor[t];
-      it.factor[t] = alpha * fji + s;
-      it.batch[t] = 0.f;
+  const int i0 = ti * 32, j0 = tj * 32;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int iu = i0 + r, ju = j0 + tx;   // upper tile (ti, tj)
+    A[r][tx] = (iu < d && ju < d) ? it.batch[(int64_t)iu * d + ju] : 0.f;
+    const int il = j0 + r, jl = i0 + tx;   // mirror tile (tj, ti)
+    B[r][tx] = (il < d && jl < d) ? it.batch[(int64_t)il * d + jl] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    {
+      const int i = i0 + r, j = j0 + tx;
+      if (i < d && j < d) {
+        const int64_t idx = (int64_t)i * d + j;
+        const float s = beta * (A[r][tx] + B[tx][r]);
+        const float f = it.first ? (i == j ? 1.f : 0.f) : it.factor[idx];
+        it.factor[idx] = alpha * f + s;
+        it.batch[idx] = 0.f;
+      }
+    }
+    if (ti != tj) {
+      const int i = j0 + r, j = i0 + tx;
+      if (i < d && j < d) {
+        const int64_t idx = (int64_t)i * d + j;
+        const float s = beta * (A[tx][r] + B[r][tx]);
+        const float f = it.first ? 0.f : it.factor[idx];
+        it.factor[idx] = alpha * f + s;
+        it.batch[idx] = 0.f;
+      }
     }
   }
 }
@@ -350,18 +383,20 @@ extern "C" int kfac_factor_conv2d_gradout(const void* g, int dtype, int batch, i
 extern "C" int kfac_factor_ema(const kfac_ema_item* items, int count, float alpha, void* stream) {
   KFAC_CHECK_ARG(count >= 0 && (items || count == 0), "items");
   cudaStream_t s = (cudaStream_t)stream;
-  for (int base = 0; base < count; base += 48) {
+  for (int base = 0; base < count; base += 40) {
     EmaBatch eb{};
-    eb.count = min(48, count - base);
+    eb.count = min(40, count - base);
     eb.alpha = alpha;
-    int dmax = 0;
+    int blocks = 0;
     for (int i = 0; i < eb.count; ++i) {
       eb.it[i] = items[base + i];
       KFAC_CHECK_ARG(eb.it[i].factor && eb.it[i].batch && eb.it[i].d > 0, "ema item");
-      dmax = max(dmax, eb.it[i].d);
+      eb.first_block[i] = blocks;
+      const int T = (eb.it[i].d + 31) / 32;
+      blocks += T * (T + 1) / 2;
     }
-    dim3 grid(min(ceil_div((int64_t)dmax * dmax, 256), 1024), eb.count);
-    ema_kernel<<<grid, 256, 0, s>>>(eb);
+    eb.first_block[eb.count] = blocks;
+    ema_kernel<<<blocks, 256, 0, s>>>(eb);
     KFAC_LAUNCH_CHECK();
   }
   return KFAC_OK;

@@ -25,11 +25,12 @@ struct TcParams {
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
   float* peerD[7]; int npeer;
+  int64_t slab_stride;             // != 0: split sp writes to D + sp * slab_stride (plain stores, no atomics)
 };
 
 struct GemmPolicy {
   using Params = TcParams;
-  struct Item { int m0, n0, kb0, kb1, diag; };
+  struct Item { int m0, n0, kb0, kb1, diag, sp; };
   static constexpr int BN = TBN;
   static constexpr bool B_IS_A = false;
   static constexpr uint32_t TX_BYTES = 2 * tc::PTILE;
@@ -46,7 +47,7 @@ struct GemmPolicy {
       while (t >= p.tiles_n - tm) { t -= p.tiles_n - tm; ++tm; }
       tn = tm + t;
     } else { tm = tile / p.tiles_n; tn = tile % p.tiles_n; }
-    it.m0 = tm * TBM; it.n0 = tn * TBN; it.diag = (tm == tn);
+    it.m0 = tm * TBM; it.n0 = tn * TBN; it.diag = (tm == tn); it.sp = sp;
     const int kb_total = ((p.K + TBK - 1) / TBK) * p.kbatch;
     const int per = (kb_total + p.splits - 1) / p.splits;
     it.kb0 = sp * per; it.kb1 = min(kb_total, it.kb0 + per);
@@ -64,7 +65,7 @@ struct GemmPolicy {
     const int m = it.m0 + row, nb = it.n0 + col0;
     if (m >= p.M || nb >= p.N) return;
     const bool mirror = p.upper_only && !it.diag;
-    float* drow = p.D + (int64_t)m * p.ldd + nb;
+    float* drow = p.D + (int64_t)it.sp * p.slab_stride + (int64_t)m * p.ldd + nb;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float x = p.alpha * v[j];
@@ -211,11 +212,13 @@ int launch_tc_gemm(const TcGemmArgs& a, cudaStream_t stream) {
     if (a.atomic && ntiles < num_sms) splits = std::max(1, std::min(num_sms / ntiles, kb_total / 8));
   }
   splits = std::max(1, std::min(splits, kb_total));
-  if (splits > 1 && !a.atomic) { set_error("tc_gemm: split-K needs atomic accumulation"); return KFAC_ERR_BAD_ARG; }
+  if (splits > 1 && !a.atomic && !a.slab) { set_error("tc_gemm: split-K needs atomic accumulation or a slab workspace"); return KFAC_ERR_BAD_ARG; }
+  if (a.slab && (a.atomic || a.upper_only || a.npeer > 0 || a.epi != EPI_NONE || a.accumulate)) { set_error("tc_gemm: slab split-K needs the plain epilogue"); return KFAC_ERR_BAD_ARG; }
   // make every split non-empty
   const int per = ceil_div(kb_total, splits);
   splits = ceil_div(kb_total, per);
   p.splits = splits;
+  if (a.slab) { p.D = a.slab; p.slab_stride = a.slab_stride; }
   const int total = ntiles * splits;
   const int grid = std::min(total, num_sms);
   tc::pipeline_kernel<GemmPolicy><<<grid, tc::PTHREADS, tc::PSMEM, stream>>>(p, total);

@@ -2,6 +2,9 @@
 // precondition, kl-clip scale and in-place gradient write-back.
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace kfac {
@@ -22,18 +25,31 @@ __global__ void gather_grad_kernel(const void* w, const void* b, int dtype, int 
   }
 }
 
-// vg += sum(P * grad)  (double accumulation, one atomic per block)
-__global__ void vg_kernel(const float* P, int ldp, const void* w, const void* b, int dtype, int g, int a,
-                          double* vg) {
-  const int aw = b ? a - 1 : a;
-  const int64_t total = (int64_t)g * a;
+// ---- kl-clip scale and write-back: ONE launch each over all layers, deterministic ---------------
+// device copy of a kfac_grad_item + the offset of its g*a elements in the concatenated element space
+struct GradDev { const float* P; void* w; void* b; int dtype, g, a, ldp; long long elem0; };
+constexpr int VG_BLOCKS = 592;          // 4 per SM; partial sums are combined in a fixed order
+
+__device__ __forceinline__ int find_item(const GradDev* items, int count, long long e) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (items[mid].elem0 <= e) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+// partials[block] = sum over the block's contiguous element range of P * grad (double accumulation);
+// the assignment of elements to threads and the reduction tree are fixed -> bitwise reproducible
+__global__ void __launch_bounds__(256) vg_all_kernel(const GradDev* items, int count, long long total, double* partials) {
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long e0 = (long long)blockIdx.x * per, e1 = min(total, e0 + per);
   double acc = 0.0;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = idx / a;
-    const int j = (int)(idx % a);
-    const float gr = (j < aw) ? load_as_float(w, dtype, i * aw + j) : load_as_float(b, dtype, i);
-    acc += (double)P[i * ldp + j] * (double)gr;
+  for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+    const GradDev& it = items[find_item(items, count, e)];
+    const long long loc = e - it.elem0;
+    const long long i = loc / it.a;
+    const int j = (int)(loc % it.a);
+    const int aw = it.b ? it.a - 1 : it.a;
+    const float gr = (j < aw) ? load_as_float(it.w, it.dtype, i * aw + j) : load_as_float(it.b, it.dtype, i);
+    acc += (double)it.P[i * it.ldp + j] * (double)gr;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -42,30 +58,32 @@ __global__ void vg_kernel(const float* P, int ldp, const void* w, const void* b,
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
-    atomicAdd(vg, t);
+    for (int k = 0; k < 8; ++k) t += red[k];
+    partials[blockIdx.x] = t;
   }
 }
 
-__global__ void nu_kernel(const double* vg, float kl_clip, float lr, float* out) {
-  const double v = (*vg) * (double)lr * (double)lr;
+__global__ void nu_kernel(const double* partials, int n, float kl_clip, float lr, double* vg_out, float* out) {
+  double vg = 0.0;
+  for (int i = 0; i < n; ++i) vg += partials[i];
+  *vg_out = vg;
+  const double v = vg * (double)lr * (double)lr;
   float nu = 1.f;
   if (v != 0.0) nu = (float)fmin(1.0, sqrt((double)kl_clip / fabs(v)));
   *out = nu;
 }
 
-__global__ void update_kernel(const float* P, int ldp, void* w, void* b, int dtype, int g, int a,
-                              const float* scale) {
-  const int aw = b ? a - 1 : a;
+__global__ void __launch_bounds__(256) update_all_kernel(const GradDev* items, int count, long long total, const float* scale) {
   const float s = scale ? *scale : 1.f;
-  const int64_t total = (int64_t)g * a;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = idx / a;
-    const int j = (int)(idx % a);
-    const float v = s * P[i * ldp + j];
-    if (j < aw) store_from_float(w, dtype, i * aw + j, v);
-    else store_from_float(b, dtype, i, v);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const GradDev& it = items[find_item(items, count, e)];
+    const long long loc = e - it.elem0;
+    const long long i = loc / it.a;
+    const int j = (int)(loc % it.a);
+    const int aw = it.b ? it.a - 1 : it.a;
+    const float v = s * it.P[i * it.ldp + j];
+    if (j < aw) store_from_float(it.w, it.dtype, i * aw + j, v);
+    else store_from_float(it.b, it.dtype, i, v);
   }
 }
 
@@ -115,8 +133,20 @@ __global__ void peer_scatter_kernel(const float* D, int64_t total, float* p0, fl
   }
 }
 
+// D[m][n] = sum_sp slab[sp][m][n] (fixed order) -- second half of the deterministic split-K
+__global__ void reduce_slabs_kernel(const float* slab, int64_t slab_stride, int splits, float* D, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    float t = slab[idx];
+    for (int sp = 1; sp < splits; ++sp) t += slab[(int64_t)sp * slab_stride + idx];
+    D[idx] = t;
+  }
+}
+
+// slab / slab_floats: optional workspace for a DETERMINISTIC split-K (partial tiles stored per split, then summed
+// in a fixed order); without it long reductions use atomic accumulation (order not reproducible).
 int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
-            int K, const Epi& e, cudaStream_t s, float* const* peers = nullptr, int npeer = 0) {
+            int K, const Epi& e, cudaStream_t s, float* const* peers = nullptr, int npeer = 0, float* slab = nullptr,
+            size_t slab_floats = 0) {
   TcGemmArgs t{};
   t.npeer = 0;
   t.A = A; t.lda = lda; t.B = B; t.ldb = ldb; t.D = D; t.ldd = ldd; t.M = M; t.N = N; t.K = K;
@@ -129,12 +159,23 @@ int gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, 
       return launch_tc_gemm(t, s);
     }
     if (e.kind == EPI_NONE && K > 1024) {
-      // long reductions: split K across CTAs and add the partial tiles with (round-to-
-      // nearest) L2 atomics -- the tensor-core accumulator truncates, so short chains
+      // long reductions are split across CTAs: the tensor-core accumulator truncates, so short chains
       // keep the 3xTF32 result at fp32 accuracy, and small tile counts fill the SMs.
+      const int splits = ceil_div(K, 512);
+      const int64_t stride = (int64_t)M * ldd;
+      if (slab && slab_floats >= (size_t)splits * stride) {
+        // deterministic: every split stores its partial tile, a second pass adds them in a fixed order
+        t.slab = slab; t.slab_stride = stride; t.splits = splits;
+        const int rc = launch_tc_gemm(t, s);
+        if (rc) return rc;
+        reduce_slabs_kernel<<<grid_for(stride), 256, 0, s>>>(slab, stride, splits, D, stride);
+        KFAC_LAUNCH_CHECK();
+        return KFAC_OK;
+      }
+      // no workspace: partial tiles are added with (round-to-nearest) L2 atomics
       KFAC_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, s));
       t.atomic = 1;
-      t.splits = ceil_div(K, 512);
+      t.splits = splits;
     }
     return launch_tc_gemm(t, s);
   }
@@ -189,11 +230,23 @@ extern "C" int kfac_transpose(const float* src, int ld_src, float* dst, int ld_d
   return KFAC_OK;
 }
 
-extern "C" size_t kfac_precondition_workspace_bytes(const kfac_precond_item* items, int count) {
+static size_t precond_slab_bytes(const kfac_precond_item* items, int count) {
+  size_t mx = 0;
+  for (int i = 0; i < count; ++i) {
+    const size_t a = items[i].a, g = items[i].g;
+    if (a > 1024) mx = std::max(mx, (size_t)ceil_div(a, 512) * a * ld4((int)g));   // GEMMs (1), (3): a x g, K = a
+    if (g > 1024) mx = std::max(mx, (size_t)ceil_div(g, 512) * g * ld4((int)a));   // GEMM (4): g x a, K = g
+  }
+  return align_up(mx * sizeof(float), 256);
+}
+static size_t precond_tile_bytes(const kfac_precond_item* items, int count) {
   size_t mx = 0;
   for (int i = 0; i < count; ++i)
     mx = std::max(mx, std::max((size_t)items[i].g * ld4(items[i].a), (size_t)items[i].a * ld4(items[i].g)));
-  return align_up(mx * sizeof(float), 256) * 3;
+  return align_up(mx * sizeof(float), 256);
+}
+extern "C" size_t kfac_precondition_workspace_bytes(const kfac_precond_item* items, int count) {
+  return precond_tile_bytes(items, count) * 3 + precond_slab_bytes(items, count);
 }
 
 extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int method, float damping,
@@ -207,10 +260,14 @@ extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int 
     return KFAC_ERR_WORKSPACE;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t slab = need / 3;
+  const size_t slab = precond_tile_bytes(items, count);
   float* GR = (float*)ws;                          // grad      g x a   (ld4(a))
   float* T1 = (float*)((char*)ws + slab);          // T^T / U^T a x g   (ld4(g))
   float* T2 = (float*)((char*)ws + 2 * slab);      // V2        g x a   (ld4(a))
+  // partial tiles of the deterministic split-K (every replica that preconditions a layer locally must get
+  // the same bits: COMM-OPT never re-synchronises the preconditioned gradients)
+  float* SK = (float*)((char*)ws + 3 * slab);
+  const size_t sk_floats = precond_slab_bytes(items, count) / sizeof(float);
   for (int i = 0; i < count; ++i) {
     const kfac_precond_item& it = items[i];
     KFAC_CHECK_ARG(it.wgrad && it.P && it.g > 0 && it.a > 0 && it.ldp >= it.a, "precond item");
@@ -226,16 +283,16 @@ extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int 
       }
       KFAC_CHECK_ARG(it.ldqa >= a && it.ldqg >= g, "eigenbasis leading dims");
       // (1) T^T[a', r] = sum_k QaT[a', k] grad[r, k]                     (a x g)
-      if ((rc = gemm_tn(it.qaT, it.ldqa, GR, lga, T1, lag, a, g, a, Epi{}, s))) return rc;
+      if ((rc = gemm_tn(it.qaT, it.ldqa, GR, lga, T1, lag, a, g, a, Epi{}, s, nullptr, 0, SK, sk_floats))) return rc;
       // (2) V2[g', a'] = (sum_k QgT[g', k] T^T[a', k]) * dgda[g', a']     (g x a)
       Epi e;
       if (it.dgda) { e.kind = EPI_MUL; e.E = it.dgda; e.lde = it.ld_dgda; }
       else { e.kind = EPI_DIV_OUTER; e.dg = it.dg; e.da = it.da; e.damping = damping; }
       if ((rc = gemm_tn(it.qgT, it.ldqg, T1, lag, T2, lga, g, a, g, e, s))) return rc;
       // (3) U^T[c, g'] = sum_k Qa[c, k] V2[g', k]                         (a x g)
-      if ((rc = gemm_tn(it.qa, it.ldqa, T2, lga, T1, lag, a, g, a, Epi{}, s))) return rc;
+      if ((rc = gemm_tn(it.qa, it.ldqa, T2, lga, T1, lag, a, g, a, Epi{}, s, nullptr, 0, SK, sk_floats))) return rc;
       // (4) P[r, c] = sum_k Qg[r, k] U^T[c, k]                            (g x a)
-      if ((rc = gemm_tn(it.qg, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers))) return rc;
+      if ((rc = gemm_tn(it.qg, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers, SK, sk_floats))) return rc;
     } else {
       if (!(it.a_inv && it.g_inv)) {
         set_error("precondition: A and G have not been inverted");
@@ -243,41 +300,63 @@ extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int 
       }
       KFAC_CHECK_ARG(it.ldqa >= a && it.ldqg >= g, "inverse leading dims");
       // the damped inverses are symmetric: T^T = Ainv grad^T, P = Ginv T
-      if ((rc = gemm_tn(it.a_inv, it.ldqa, GR, lga, T1, lag, a, g, a, Epi{}, s))) return rc;
-      if ((rc = gemm_tn(it.g_inv, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers))) return rc;
+      if ((rc = gemm_tn(it.a_inv, it.ldqa, GR, lga, T1, lag, a, g, a, Epi{}, s, nullptr, 0, SK, sk_floats))) return rc;
+      if ((rc = gemm_tn(it.g_inv, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers, SK, sk_floats))) return rc;
     }
   }
   return KFAC_OK;
 }
 
-extern "C" int kfac_grad_scale(const kfac_grad_item* items, int count, float kl_clip, float lr,
-                               double* scratch, float* scale_out, void* stream) {
-  KFAC_CHECK_ARG(count >= 0 && (items || count == 0) && scratch && scale_out, "grad_scale args");
-  cudaStream_t s = (cudaStream_t)stream;
-  KFAC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), s));
+extern "C" size_t kfac_grad_workspace_bytes(int count) {
+  return align_up(sizeof(GradDev) * (size_t)std::max(1, count), 256) + align_up(sizeof(double) * (VG_BLOCKS + 1), 256);
+}
+
+// uploads the item table into the workspace; returns the total number of gradient elements
+static int upload_grad_items(const kfac_grad_item* items, int count, void* ws, size_t ws_bytes, cudaStream_t s,
+                             long long* total_out) {
+  if (!ws || ws_bytes < kfac_grad_workspace_bytes(count)) {
+    set_error("grad scale/update: workspace too small (%zu < %zu)", ws_bytes, kfac_grad_workspace_bytes(count));
+    return KFAC_ERR_WORKSPACE;
+  }
+  std::vector<GradDev> dev(count);
+  long long total = 0;
   for (int i = 0; i < count; ++i) {
     const kfac_grad_item& it = items[i];
     KFAC_CHECK_ARG(it.P && it.wgrad && it.g > 0 && it.a > 0 && it.ldp >= it.a, "grad item");
-    vg_kernel<<<grid_for((int64_t)it.g * it.a), 256, 0, s>>>(it.P, it.ldp, it.wgrad, it.bgrad, it.grad_dtype,
-                                                            it.g, it.a, scratch);
+    dev[i] = GradDev{it.P, it.wgrad, it.bgrad, it.grad_dtype, it.g, it.a, it.ldp, total};
+    total += (long long)it.g * it.a;
   }
-  count_launch(count - 1);
-  KFAC_LAUNCH_CHECK();
-  nu_kernel<<<1, 1, 0, s>>>(scratch, kl_clip, lr, scale_out);
+  KFAC_CUDA(cudaMemcpyAsync(ws, dev.data(), sizeof(GradDev) * count, cudaMemcpyHostToDevice, s));   // pageable: staged
+  *total_out = total;
+  return KFAC_OK;
+}
+
+extern "C" int kfac_grad_scale(const kfac_grad_item* items, int count, float kl_clip, float lr, void* ws,
+                               size_t ws_bytes, float* scale_out, void* stream) {
+  KFAC_CHECK_ARG(count >= 0 && (items || count == 0) && scale_out, "grad_scale args");
+  cudaStream_t s = (cudaStream_t)stream;
+  long long total = 0;
+  if (count > 0) { const int rc = upload_grad_items(items, count, ws, ws_bytes, s, &total); if (rc) return rc; }
+  else if (!ws || ws_bytes < kfac_grad_workspace_bytes(0)) { set_error("grad_scale: workspace"); return KFAC_ERR_WORKSPACE; }
+  double* partials = (double*)((char*)ws + align_up(sizeof(GradDev) * (size_t)std::max(1, count), 256));
+  const int nblk = (int)std::max<long long>(1, std::min<long long>(VG_BLOCKS, (total + 255) / 256));
+  if (count > 0) {
+    vg_all_kernel<<<nblk, 256, 0, s>>>((const GradDev*)ws, count, total, partials);
+    KFAC_LAUNCH_CHECK();
+  }
+  nu_kernel<<<1, 1, 0, s>>>(partials, count > 0 ? nblk : 0, kl_clip, lr, partials + VG_BLOCKS, scale_out);
   KFAC_LAUNCH_CHECK();
   return KFAC_OK;
 }
 
-extern "C" int kfac_grad_update(const kfac_grad_item* items, int count, const float* scale, void* stream) {
+extern "C" int kfac_grad_update(const kfac_grad_item* items, int count, const float* scale, void* ws,
+                                size_t ws_bytes, void* stream) {
   KFAC_CHECK_ARG(count >= 0 && (items || count == 0), "grad_update args");
+  if (count == 0) return KFAC_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  for (int i = 0; i < count; ++i) {
-    const kfac_grad_item& it = items[i];
-    KFAC_CHECK_ARG(it.P && it.wgrad && it.g > 0 && it.a > 0 && it.ldp >= it.a, "grad item");
-    update_kernel<<<grid_for((int64_t)it.g * it.a), 256, 0, s>>>(it.P, it.ldp, it.wgrad, it.bgrad, it.grad_dtype,
-                                                                it.g, it.a, scale);
-  }
-  count_launch(count - 1);
+  long long total = 0;
+  { const int rc = upload_grad_items(items, count, ws, ws_bytes, s, &total); if (rc) return rc; }
+  update_all_kernel<<<grid_for(total), 256, 0, s>>>((const GradDev*)ws, count, total, scale);
   KFAC_LAUNCH_CHECK();
   return KFAC_OK;
 }

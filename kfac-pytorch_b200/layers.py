@@ -66,6 +66,23 @@ class ModuleHelper:
         raise NotImplementedError
 
 
+_NATIVE_INPUT_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
+
+
+def cast_for_factor(t: torch.Tensor, factor_dtype: torch.dtype | None) -> torch.Tensor:
+    """The reference casts the activation / grad-output to `factor_dtype` before the statistics are formed
+    (kfac/layers/base.py:350,364).  Here the statistics are always ACCUMULATED and STORED in float32:
+      * float16 / bfloat16: the input is rounded to that dtype (same input rounding as the reference),
+        the products are accumulated in fp32 (at least as accurate as the reference's half GEMM);
+      * float32 / float64 / None: the input is used as is (float64 inputs are cast to float32 at the
+        boundary -- the native library has no fp64 path; documented deviation)."""
+    if factor_dtype in (torch.float16, torch.bfloat16) and t.dtype != factor_dtype:
+        t = t.to(factor_dtype)
+    if t.dtype not in _NATIVE_INPUT_DTYPES:
+        t = t.to(torch.float32)
+    return t
+
+
 def _dtype_code(t: torch.Tensor) -> int:
     try:
         return _cabi.DTYPE_CODE[t.dtype]
@@ -221,19 +238,26 @@ class KFACLayer:
         return f'{self.__class__.__name__}({repr(self.module)})'
 
     # -------- reference-compatible read accessors (views into the arenas)
+    def _as_factor_dtype(self, t):
+        fd = self.factor_dtype
+        return t if (t is None or fd in (None, torch.float32)) else t.to(fd)
+
     @property
     def a_factor(self):
-        return self._a_view if self._has_a else None
+        """Running average A (fp32 arena view; a cast copy when `factor_dtype` is not float32)."""
+        return self._as_factor_dtype(self._a_view if self._has_a else None)
 
     @property
     def g_factor(self):
-        return self._g_view if self._has_g else None
+        return self._as_factor_dtype(self._g_view if self._has_g else None)
 
     def _inv_get(self, key):
         if key not in self._inv_ready:
             return None
         t = self._inv[key]
-        return t[:, :self._inv_cols[key]] if t.dim() == 2 else t
+        t = t[:, :self._inv_cols[key]] if t.dim() == 2 else t
+        # second-order data is stored in fp32; `inv_dtype=float64` readers get a cast copy (eigen.py:319-320)
+        return t if self.inv_dtype == torch.float32 else t.to(self.inv_dtype)
 
     qa = property(lambda self: self._inv_get('qa'))
     qg = property(lambda self: self._inv_get('qg'))
@@ -249,7 +273,8 @@ class KFACLayer:
         return self._p_view if self._grad_ready else None
 
     def state_dict(self) -> dict[str, torch.Tensor | None]:
-        return {'A': self.a_factor, 'G': self.g_factor}
+        a, g = self.a_factor, self.g_factor
+        return {'A': a.clone() if a is not None else None, 'G': g.clone() if g is not None else None}
 
     def load_state_dict(self, state_dict: dict[str, torch.Tensor | None]) -> None:
         if 'A' not in state_dict or 'G' not in state_dict:

@@ -68,11 +68,16 @@ class KFACPreconditioner(BaseKFACPreconditioner):
         if (compute_method == ComputeMethod.EIGEN and compute_eigenvalue_outer_product
                 and not colocate_factors):
             raise ValueError('colocate_factors must be True to use compute_eigenvalue_outer_product')
-        if factor_dtype not in (None, torch.float32) or inv_dtype != torch.float32:
+        # factors and second-order data are STORED in float32 arenas (tensor-core 3xTF32 with fp32
+        # accumulation has no fp64 path): float64 is accepted and cast at the boundary, half-precision
+        # factor dtypes round the hook inputs like the reference does (kfac/layers/base.py:350,364)
+        if factor_dtype not in (None, torch.float32, torch.float64, torch.float16, torch.bfloat16):
+            raise ValueError(f'unsupported factor_dtype {factor_dtype}')
+        if inv_dtype not in (torch.float32, torch.float64):
             raise ValueError(
-                'kfac_b200 keeps factors and second-order data in float32 (tensor-core '
-                '3xTF32 / fp32 accumulate); factor_dtype / inv_dtype other than float32 '
-                'are not supported')
+                'kfac_b200 computes the eigendecompositions and the precondition in float32 (like '
+                'kfac/layers/eigen.py:310-312); inv_dtype must be float32 or float64 (cast at the boundary), '
+                f'got {inv_dtype}')
 
         size = get_world_size()
         if isinstance(grad_worker_fraction, DistributedStrategy):

@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")/../.."
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 mkdir -p tests/host/bin
-for t in jacobi_systolic_gpu:jsys_gpu ema_tiled_gpu:ema_gpu; do
+for t in jacobi_systolic_gpu:jsys_gpu; do
   src=${t%%:*}; out=${t##*:}
   $NVCC -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I include tests/host/$src.cu \
         -L kfac-pytorch_b200/csrc -lkfac_b200 -o tests/host/bin/$out

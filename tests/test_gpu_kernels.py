@@ -330,8 +330,10 @@ def test_precondition_and_update(lib, dev, g, a, bias, method):
     gi[0] = _cabi.GradItem(Ps.data_ptr(), wd.data_ptr(), bd.data_ptr() if bias else None, 0, g, a, lda_)
     vg = torch.zeros(1, dtype=torch.float64, device=dev)
     nu = torch.zeros(1, device=dev)
-    assert lib.kfac_grad_scale(gi, 1, 0.001, 0.1, vg.data_ptr(), nu.data_ptr(), S()) == 0
-    assert lib.kfac_grad_update(gi, 1, nu.data_ptr(), S()) == 0
+    gneed = lib.kfac_grad_workspace_bytes(1)
+    gws = torch.empty(gneed, dtype=torch.uint8, device=dev)
+    assert lib.kfac_grad_scale(gi, 1, 0.001, 0.1, gws.data_ptr(), gneed, nu.data_ptr(), S()) == 0
+    assert lib.kfac_grad_update(gi, 1, nu.data_ptr(), gws.data_ptr(), gneed, S()) == 0
     torch.cuda.synchronize()
     ref_scale = O.grad_scale([ref], [grad], 0.1, 0.001)
     assert abs(float(nu) - ref_scale) <= 1e-4 * ref_scale
