@@ -253,3 +253,72 @@ def test_grad_scaler_unscales_g_factor():
         outs.append([q.grad.clone() for q in m.parameters()])
     for a, b in zip(*outs):
         assert rel_fro(a, b) < 1e-4
+
+
+def test_cross_load_reference_checkpoint():
+    """A state_dict WRITTEN BY THE UNMODIFIED REFERENCE (tests/golden/ref_checkpoint.pt, generated by
+    oracle/gen_golden_ckpt.py; schema of kfac/base_preconditioner.py:215-247) loads into the CUDA preconditioner,
+    and the step right after loading reproduces what the reference itself computes after loading it
+    (inverses recomputed from the loaded factors on load, kfac/base_preconditioner.py:296-308)."""
+    from conftest import load_fixture
+    from kfac_b200.preconditioner import KFACPreconditioner
+    from workloads import SmallConvNet
+    fx = load_fixture('ref_checkpoint')
+    dev = torch.device('cuda:0')
+    model = SmallConvNet()
+    model.load_state_dict(fx['weights'])
+    model.to(dev)
+    pre = KFACPreconditioner(model, **fx['kwargs'])
+    pre.load_state_dict(fx['state_dict'])
+    assert pre.steps == fx['state_dict']['steps'] == 3
+    # round trip: what we write back has the reference's schema and the same factors
+    sd = pre.state_dict()
+    assert set(sd) == set(fx['state_dict'])
+    assert set(sd['layers']) == set(fx['state_dict']['layers'])
+    for name, st in fx['state_dict']['layers'].items():
+        assert set(sd['layers'][name]) == {'A', 'G'}
+        assert rel_fro(sd['layers'][name]['A'], st['A']) < 1e-7 and rel_fro(sd['layers'][name]['G'], st['G']) < 1e-7
+    x, y = fx['batch']
+    model.zero_grad()
+    torch.nn.CrossEntropyLoss()(model(x.to(dev)), y.to(dev)).backward()
+    pre.step()
+    torch.cuda.synchronize()
+    layers = {n: l for n, l in pre._layers.values()}
+    for name, g in fx['after']['layers'].items():
+        L = layers[name]
+        assert rel_fro(L.a_factor, g['A']) < 2e-5 and rel_fro(L.g_factor, g['G']) < 2e-5, name
+        assert rel_fro(L._p_view, g['P']) < 1e-3, (name, rel_fro(L._p_view, g['P']))
+    assert abs(pre._compute_grad_scale() - fx['after']['scale']) <= 1e-3 * abs(fx['after']['scale'])
+    for n, p in model.named_parameters():
+        assert rel_fro(p.grad, fx['after']['final_grads'][n]) < 1e-3, n
+    # and a state dict written here is accepted by the oracle-side schema check: tensors, fp32, square
+    for name, st in sd['layers'].items():
+        assert st['A'].dtype == torch.float32 and st['A'].shape[0] == st['A'].shape[1]
+
+
+def test_factor_and_inv_dtype_are_accepted():
+    """factor_dtype / inv_dtype (kfac/layers/base.py:350,364; eigen.py:319-320): fp64 is cast at the boundary
+    (fp32 storage and arithmetic), bf16 rounds the hook inputs like the reference does."""
+    from kfac_b200.preconditioner import KFACPreconditioner
+    from workloads import TinyModel
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    base = TinyModel().to(dev)
+    x = torch.rand(8, 10, device=dev)
+    grads = {}
+    for fd, idt in ((None, torch.float32), (torch.float64, torch.float64), (torch.bfloat16, torch.float32)):
+        m = copy.deepcopy(base)
+        p = KFACPreconditioner(m, factor_dtype=fd, inv_dtype=idt)
+        m(x).sum().backward()
+        p.step()
+        torch.cuda.synchronize()
+        layer = p._layers[m.linear1][1]
+        assert layer.a_factor.dtype == (fd or torch.float32)
+        assert layer.qa.dtype == idt
+        grads[fd] = [q.grad.clone() for q in m.parameters()]
+    for a, b in zip(grads[None], grads[torch.float64]):
+        assert torch.equal(a, b)                  # fp64 request = fp32 arithmetic, identical bits
+    for a, b in zip(grads[None], grads[torch.bfloat16]):
+        assert rel_fro(a, b) < 5e-2               # bf16-rounded statistics
+    with pytest.raises(ValueError):
+        KFACPreconditioner(copy.deepcopy(base), inv_dtype=torch.float16)
