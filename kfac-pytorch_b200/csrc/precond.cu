@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gemm_grouped.cuh"
 
 namespace kfac {
 
@@ -22,6 +23,24 @@ __global__ void gather_grad_kernel(const void* w, const void* b, int dtype, int 
     if (j < aw) v = load_as_float(w, dtype, i * aw + j);
     else if (j < a) v = load_as_float(b, dtype, i);
     out[idx] = v;
+  }
+}
+
+// all layers in one launch: item i owns the elements [elem0, elem0 + g * ldo) of the concatenated space
+struct GatherDev { const void* w; const void* b; int dtype, g, a, ldo; float* out; long long elem0; };
+__global__ void __launch_bounds__(256) gather_all_kernel(const GatherDev* items, int count, long long total) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = count - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (items[mid].elem0 <= e) lo = mid; else hi = mid - 1; }
+    const GatherDev& it = items[lo];
+    const long long idx = e - it.elem0;
+    const long long i = idx / it.ldo;
+    const int j = (int)(idx % it.ldo);
+    const int aw = it.b ? it.a - 1 : it.a;
+    float v = 0.f;
+    if (j < aw) v = load_as_float(it.w, it.dtype, i * aw + j);
+    else if (j < it.a) v = load_as_float(it.b, it.dtype, i);
+    it.out[idx] = v;
   }
 }
 
@@ -230,23 +249,47 @@ extern "C" int kfac_transpose(const float* src, int ld_src, float* dst, int ld_d
   return KFAC_OK;
 }
 
-static size_t precond_slab_bytes(const kfac_precond_item* items, int count) {
-  size_t mx = 0;
+// ---- precondition: stage-wise over ALL layers ------------------------------------------------------
+// workspace: [GatherDev table][grouped-GEMM tables][per layer: GR (g x ld4 a), T1 (a x ld4 g), T2 (g x ld4 a)][slabs]
+struct PrecondLayout {
+  size_t off_gather, off_gemm, off_tiles, off_slab, total;
+  std::vector<size_t> gr, t1, t2, slab_a, slab_g;     // byte offsets per layer (slab_*: 0 = no split)
+  std::vector<int> splits_a, splits_g;
+};
+
+static void precond_layout(const kfac_precond_item* items, int count, PrecondLayout& L) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.off_gather = take(sizeof(GatherDev) * (size_t)std::max(1, count));
+  L.off_gemm = take(grouped_gemm_ws_bytes(count));
+  L.off_tiles = off;
+  L.gr.resize(count); L.t1.resize(count); L.t2.resize(count);
+  L.slab_a.assign(count, 0); L.slab_g.assign(count, 0); L.splits_a.assign(count, 1); L.splits_g.assign(count, 1);
   for (int i = 0; i < count; ++i) {
     const size_t a = items[i].a, g = items[i].g;
-    if (a > 1024) mx = std::max(mx, (size_t)ceil_div(a, 512) * a * ld4((int)g));   // GEMMs (1), (3): a x g, K = a
-    if (g > 1024) mx = std::max(mx, (size_t)ceil_div(g, 512) * g * ld4((int)a));   // GEMM (4): g x a, K = g
+    L.gr[i] = take(g * ld4((int)a) * sizeof(float));
+    L.t1[i] = take(a * ld4((int)g) * sizeof(float));
+    L.t2[i] = take(g * ld4((int)a) * sizeof(float));
   }
-  return align_up(mx * sizeof(float), 256);
+  L.off_slab = off;
+  // long reductions (K > 1024) are split into chains of <= 512: the tensor-core accumulator truncates, short
+  // chains keep the 3xTF32 result at fp32 accuracy; the partial tiles go to slabs and are added in a fixed order
+  // (deterministic: every replica that preconditions a layer locally must get the same bits)
+  for (int i = 0; i < count; ++i) {
+    const size_t a = items[i].a, g = items[i].g;
+    if (a > 1024) { L.splits_a[i] = ceil_div(a, 512); L.slab_a[i] = take((size_t)L.splits_a[i] * a * ld4((int)g) * sizeof(float)); }
+    if (g > 1024 && items[i].n_peers == 0) {
+      L.splits_g[i] = ceil_div(g, 512); L.slab_g[i] = take((size_t)L.splits_g[i] * g * ld4((int)a) * sizeof(float));
+    }
+  }
+  L.total = off;
 }
-static size_t precond_tile_bytes(const kfac_precond_item* items, int count) {
-  size_t mx = 0;
-  for (int i = 0; i < count; ++i)
-    mx = std::max(mx, std::max((size_t)items[i].g * ld4(items[i].a), (size_t)items[i].a * ld4(items[i].g)));
-  return align_up(mx * sizeof(float), 256);
-}
+
 extern "C" size_t kfac_precondition_workspace_bytes(const kfac_precond_item* items, int count) {
-  return precond_tile_bytes(items, count) * 3 + precond_slab_bytes(items, count);
+  if (count <= 0) return 0;
+  PrecondLayout L;
+  precond_layout(items, count, L);
+  return L.total;
 }
 
 extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int method, float damping,
@@ -254,57 +297,85 @@ extern "C" int kfac_precondition(const kfac_precond_item* items, int count, int 
   KFAC_CHECK_ARG(count >= 0 && (items || count == 0), "items");
   KFAC_CHECK_ARG(method == KFAC_EIGEN || method == KFAC_INVERSE, "method");
   if (count == 0) return KFAC_OK;
-  const size_t need = kfac_precondition_workspace_bytes(items, count);
-  if (!ws || ws_bytes < need) {
-    set_error("precondition: workspace too small (%zu < %zu)", ws_bytes, need);
+  PrecondLayout L;
+  precond_layout(items, count, L);
+  if (!ws || ws_bytes < L.total) {
+    set_error("precondition: workspace too small (%zu < %zu)", ws_bytes, L.total);
     return KFAC_ERR_WORKSPACE;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t slab = precond_tile_bytes(items, count);
-  float* GR = (float*)ws;                          // grad      g x a   (ld4(a))
-  float* T1 = (float*)((char*)ws + slab);          // T^T / U^T a x g   (ld4(g))
-  float* T2 = (float*)((char*)ws + 2 * slab);      // V2        g x a   (ld4(a))
-  // partial tiles of the deterministic split-K (every replica that preconditions a layer locally must get
-  // the same bits: COMM-OPT never re-synchronises the preconditioned gradients)
-  float* SK = (float*)((char*)ws + 3 * slab);
-  const size_t sk_floats = precond_slab_bytes(items, count) / sizeof(float);
+  char* base = (char*)ws;
+  auto F = [&](size_t off) { return (float*)(base + off); };
+  // stage 0: grad matrices [wgrad | bgrad] of all layers, one launch
+  std::vector<GatherDev> gat(count);
+  long long total = 0;
   for (int i = 0; i < count; ++i) {
     const kfac_precond_item& it = items[i];
     KFAC_CHECK_ARG(it.wgrad && it.P && it.g > 0 && it.a > 0 && it.ldp >= it.a, "precond item");
     KFAC_CHECK_ARG(it.n_peers >= 0 && it.n_peers <= 7 && (it.n_peers == 0 || it.peer_P), "precond peers");
-    const int g = it.g, a = it.a, lga = ld4(a), lag = ld4(g);
-    gather_grad_kernel<<<grid_for((int64_t)g * lga), 256, 0, s>>>(it.wgrad, it.bgrad, it.grad_dtype, g, a, GR, lga);
-    KFAC_LAUNCH_CHECK();
-    int rc;
     if (method == KFAC_EIGEN) {
       if (!(it.qa && it.qg && it.qaT && it.qgT && (it.dgda || (it.da && it.dg)))) {
         set_error("precondition: eigendecompositions for both A and G have not been computed");
         return KFAC_ERR_NOT_READY;
       }
-      KFAC_CHECK_ARG(it.ldqa >= a && it.ldqg >= g, "eigenbasis leading dims");
-      // (1) T^T[a', r] = sum_k QaT[a', k] grad[r, k]                     (a x g)
-      if ((rc = gemm_tn(it.qaT, it.ldqa, GR, lga, T1, lag, a, g, a, Epi{}, s, nullptr, 0, SK, sk_floats))) return rc;
-      // (2) V2[g', a'] = (sum_k QgT[g', k] T^T[a', k]) * dgda[g', a']     (g x a)
-      Epi e;
-      if (it.dgda) { e.kind = EPI_MUL; e.E = it.dgda; e.lde = it.ld_dgda; }
-      else { e.kind = EPI_DIV_OUTER; e.dg = it.dg; e.da = it.da; e.damping = damping; }
-      if ((rc = gemm_tn(it.qgT, it.ldqg, T1, lag, T2, lga, g, a, g, e, s))) return rc;
-      // (3) U^T[c, g'] = sum_k Qa[c, k] V2[g', k]                         (a x g)
-      if ((rc = gemm_tn(it.qa, it.ldqa, T2, lga, T1, lag, a, g, a, Epi{}, s, nullptr, 0, SK, sk_floats))) return rc;
-      // (4) P[r, c] = sum_k Qg[r, k] U^T[c, k]                            (g x a)
-      if ((rc = gemm_tn(it.qg, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers, SK, sk_floats))) return rc;
-    } else {
-      if (!(it.a_inv && it.g_inv)) {
-        set_error("precondition: A and G have not been inverted");
-        return KFAC_ERR_NOT_READY;
-      }
-      KFAC_CHECK_ARG(it.ldqa >= a && it.ldqg >= g, "inverse leading dims");
-      // the damped inverses are symmetric: T^T = Ainv grad^T, P = Ginv T
-      if ((rc = gemm_tn(it.a_inv, it.ldqa, GR, lga, T1, lag, a, g, a, Epi{}, s, nullptr, 0, SK, sk_floats))) return rc;
-      if ((rc = gemm_tn(it.g_inv, it.ldqg, T1, lag, it.P, it.ldp, g, a, g, Epi{}, s, it.peer_P, it.n_peers, SK, sk_floats))) return rc;
+    } else if (!(it.a_inv && it.g_inv)) {
+      set_error("precondition: A and G have not been inverted");
+      return KFAC_ERR_NOT_READY;
+    }
+    KFAC_CHECK_ARG(it.ldqa >= it.a && it.ldqg >= it.g, "second-order leading dims");
+    gat[i] = GatherDev{it.wgrad, it.bgrad, it.grad_dtype, it.g, it.a, ld4(it.a), F(L.gr[i]), total};
+    total += (long long)it.g * ld4(it.a);
+  }
+  KFAC_CUDA(cudaMemcpyAsync(base + L.off_gather, gat.data(), sizeof(GatherDev) * count, cudaMemcpyHostToDevice, s));
+  gather_all_kernel<<<grid_for(total), 256, 0, s>>>((const GatherDev*)(base + L.off_gather), count, total);
+  KFAC_LAUNCH_CHECK();
+
+  std::vector<GroupedGemm> st(count);
+  auto run = [&]() { return launch_grouped_gemm(st.data(), count, base + L.off_gemm, grouped_gemm_ws_bytes(count), s); };
+  auto plain = [&](int i, const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N, int K) {
+    GroupedGemm g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.D = D; g.ldd = ldd; g.M = M; g.N = N; g.K = K; g.alpha = 1.f;
+    g.epi = EPI_NONE; g.splits = 1;
+    st[i] = g;
+  };
+  int rc;
+  // the four (two) GEMMs of every layer form a chain; stage k of all layers is one grouped launch
+  for (int i = 0; i < count; ++i) {     // (1) T^T[a', r] = sum_k (QaT | Ainv)[a', k] grad[r, k]          (a x g, K = a)
+    const kfac_precond_item& it = items[i];
+    const int g = it.g, a = it.a;
+    plain(i, method == KFAC_EIGEN ? it.qaT : it.a_inv, it.ldqa, F(L.gr[i]), ld4(a), F(L.t1[i]), ld4(g), a, g, a);
+    if (L.splits_a[i] > 1) { st[i].splits = L.splits_a[i]; st[i].slab = F(L.slab_a[i]); st[i].slab_stride = (int64_t)a * ld4(g); }
+  }
+  if ((rc = run())) return rc;
+  if (method == KFAC_EIGEN) {
+    for (int i = 0; i < count; ++i) {   // (2) V2[g', a'] = (sum_k QgT[g', k] T^T[a', k]) * dgda[g', a']     (g x a, K = g)
+      const kfac_precond_item& it = items[i];
+      const int g = it.g, a = it.a;
+      plain(i, it.qgT, it.ldqg, F(L.t1[i]), ld4(g), F(L.t2[i]), ld4(a), g, a, g);
+      if (it.dgda) { st[i].epi = EPI_MUL; st[i].E = it.dgda; st[i].lde = it.ld_dgda; }
+      else { st[i].epi = EPI_DIV_OUTER; st[i].dg = it.dg; st[i].da = it.da; st[i].damping = damping; }
+    }
+    if ((rc = run())) return rc;
+    for (int i = 0; i < count; ++i) {   // (3) U^T[c, g'] = sum_k Qa[c, k] V2[g', k]                         (a x g, K = a)
+      const kfac_precond_item& it = items[i];
+      const int g = it.g, a = it.a;
+      plain(i, it.qa, it.ldqa, F(L.t2[i]), ld4(a), F(L.t1[i]), ld4(g), a, g, a);
+      if (L.splits_a[i] > 1) { st[i].splits = L.splits_a[i]; st[i].slab = F(L.slab_a[i]); st[i].slab_stride = (int64_t)a * ld4(g); }
+    }
+    if ((rc = run())) return rc;
+  }
+  for (int i = 0; i < count; ++i) {     // (4) P[r, c] = sum_k (Qg | Ginv)[r, k] U^T[c, k]                  (g x a, K = g)
+    const kfac_precond_item& it = items[i];
+    const int g = it.g, a = it.a;
+    plain(i, method == KFAC_EIGEN ? it.qg : it.g_inv, it.ldqg, F(L.t1[i]), ld4(g), it.P, it.ldp, g, a, g);
+    if (it.n_peers > 0) {               // fused compute + broadcast: no split (the tiles are final when stored)
+      st[i].npeer = it.n_peers;
+      for (int q = 0; q < it.n_peers; ++q) st[i].peerD[q] = it.peer_P[q];
+    } else if (L.splits_g[i] > 1 && it.ldp == ld4(a)) {
+      st[i].splits = L.splits_g[i]; st[i].slab = F(L.slab_g[i]); st[i].slab_stride = (int64_t)g * ld4(a);
     }
   }
-  return KFAC_OK;
+  return run();
 }
 
 extern "C" size_t kfac_grad_workspace_bytes(int count) {
