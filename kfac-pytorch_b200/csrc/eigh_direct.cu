@@ -165,6 +165,35 @@ void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
 
 }  // namespace
 
+int StreamPool::init() {
+  if (ready) return KFAC_OK;
+  for (int i = 0; i < N; ++i) {
+    KFAC_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    KFAC_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+  }
+  KFAC_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  ready = true;
+  return KFAC_OK;
+}
+int StreamPool::fork(cudaStream_t s) {
+  int rc = init();
+  if (rc) return rc;
+  KFAC_CUDA(cudaEventRecord(ev_fork, s));
+  for (int i = 0; i < N; ++i) KFAC_CUDA(cudaStreamWaitEvent(st[i], ev_fork, 0));
+  return KFAC_OK;
+}
+int StreamPool::join(cudaStream_t s) {
+  for (int i = 0; i < N; ++i) {
+    KFAC_CUDA(cudaEventRecord(ev_join[i], st[i]));
+    KFAC_CUDA(cudaStreamWaitEvent(s, ev_join[i], 0));
+  }
+  return KFAC_OK;
+}
+StreamPool& stream_pool() {
+  static thread_local StreamPool pool;     // one per calling thread (and therefore per device context in practice)
+  return pool;
+}
+
 int gemm_tn_acc(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N, int K,
                 float alpha, cudaStream_t s) {
   TcGemmArgs t{};
@@ -263,11 +292,17 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     larft_kernel<<<(int)blocks.size(), BT, lsmem, s>>>(d_blocks);
   }
   KFAC_LAUNCH_CHECK();
+  // the chains of different matrices are independent: spread them over the side streams
+  StreamPool& pool = stream_pool();
+  const bool spread = count > 1;
+  if (spread && (rc = pool.fork(s))) return rc;
+  const cudaStream_t s_main = s;
   for (int i = 0; i < count; ++i) {
     const MatLayout& m = L.m[i];
     const TrdMat& t = trd[i];
     const DcMat& d = dc[i];
     const int n = m.n, np = m.np;
+    cudaStream_t s = spread ? pool.st[i % StreamPool::N] : s_main;
     float* Z = d.Q[d.result_buf];
     float* ZT = d.Q[d.result_buf ^ 1];
     transpose_ld_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32)), dim3(32, 8), 0, s>>>(Z, np, ZT, np, n, n);
@@ -301,6 +336,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     clamp_copy_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d.d, items[i].d, n);
     KFAC_LAUNCH_CHECK();
   }
+  if (spread && (rc = pool.join(s_main))) return rc;
   return KFAC_OK;
 }
 

@@ -62,6 +62,18 @@ int launch_jacobi_direct64(EighMat* d_mats, const int* d_list, int count, cudaSt
 // plain fp32 TN GEMM on the tcgen05 engine: D = alpha * A B^T (+ D when accumulate)
 int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
                   int K, cudaStream_t s);
+// a few side streams for independent small launches (per-merge / per-matrix GEMM chains)
+struct StreamPool {
+  static constexpr int N = 4;
+  cudaStream_t st[N];
+  cudaEvent_t ev_fork, ev_join[N];
+  bool ready = false;
+  int init();
+  int fork(cudaStream_t s);     // side streams wait for everything enqueued on s so far
+  int join(cudaStream_t s);     // s waits for everything enqueued on the side streams
+};
+StreamPool& stream_pool();
+
 size_t eigh_direct_workspace_bytes(const int* n, int count);
 int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, cudaStream_t s);
 int gemm_tn_acc(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,

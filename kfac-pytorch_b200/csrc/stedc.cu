@@ -515,13 +515,20 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
     KFAC_LAUNCH_CHECK();
     dc_copy_d_kernel<<<dim3(ceil_div(mmax, 256), nm), 256, 0, s>>>(d_mats, d_levels[l]);
     KFAC_LAUNCH_CHECK();
+    // one GEMM per merge, independent of each other: spread over the side streams
+    StreamPool& pool = stream_pool();
+    const bool spread = nm > 1;
+    if (spread) { const int rc = pool.fork(s); if (rc) return rc; }
+    int gi = 0;
     for (auto& mg : lv) {
       const DcMat& mt = h_mats[mg.mat];
       const int m = mg.hi - mg.lo;
       const int64_t o = (int64_t)mg.lo * mt.ld + mg.lo;
-      const int rc = gemm_tn_plain(mt.Q[mg.src] + o, mt.ld, mt.UT + o, mt.ld, mt.Q[mg.src ^ 1] + o, mt.ld, m, m, m, s);
+      cudaStream_t gs = spread ? pool.st[gi++ % StreamPool::N] : s;
+      const int rc = gemm_tn_plain(mt.Q[mg.src] + o, mt.ld, mt.UT + o, mt.ld, mt.Q[mg.src ^ 1] + o, mt.ld, m, m, m, gs);
       if (rc) return rc;
     }
+    if (spread) { const int rc = pool.join(s); if (rc) return rc; }
   }
   for (int i = 0; i < count; ++i) h_mats[i].result_buf = pl.result_buf[i];
   return KFAC_OK;

@@ -88,7 +88,7 @@ def test_sytrd(lib, n, ncta, kind):
     assert ev < 1e-5
 
 
-@pytest.mark.parametrize('n,kind', [(64, 'rand'), (65, 'rand'), (128, 'rand'), (200, 'kfac'), (576, 'kfac'), (1000, 'rand'),
+@pytest.mark.parametrize('n,kind', [(65, 'rand'), (100, 'rand'), (128, 'rand'), (200, 'kfac'), (576, 'kfac'), (1000, 'rand'),
                                     (2049, 'kfac'), (1024, 'equal'), (4608, 'kfac'), (300, 'zero_e')])
 def test_stedc(lib, n, kind):
     dev = torch.device('cuda:0')
