@@ -128,8 +128,10 @@ double job_time(int n, int C) { return (double)n * (T0 + BETA * (double)n * n / 
 void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
   // smallest makespan M such that the CTA-time of all jobs (each sized to finish within M) fits into G * M
   auto ctas_for = [&](int ni, double M) {
-    const int cmax = std::max(1, std::min(G, (ni / TRD_T) * (ni / TRD_T + 1) / 2 / 2 + 1));   // >= 2 tiles per sub-group pays
-    for (int C = 1; C <= cmax; ++C) if (job_time(ni, C) <= M) return C;
+    const int nb = (ni + TRD_T - 1) / TRD_T;
+    const int cmin = std::min(G, sytrd_min_ctas(ni));
+    const int cmax = std::max(cmin, std::min(G, nb * (nb + 1) / 2 / 2 + 1));   // >= 2 tiles per sub-group pays
+    for (int C = cmin; C <= cmax; ++C) if (job_time(ni, C) <= M) return C;
     return cmax;
   };
   double lo = 0, hi = 0;
@@ -350,6 +352,7 @@ extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e
   const int np = round_up(n, TRD_T), nblk = np / TRD_T;
   const int G = sytrd_max_grid();
   if (ncta <= 0 || ncta > G) ncta = G;
+  ncta = std::max(ncta, std::min(G, sytrd_min_ctas(n)));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t oA = take((size_t)np * (np + 128) * 4), oVT = take((size_t)np * np * 4), oVp = take((size_t)np * TRD_NB * 4),

@@ -35,6 +35,7 @@ struct TrdJob { int mat, cta0, ncta; };
 // all jobs of one launch; a CTA processes the jobs that contain it in list order
 int launch_sytrd(const TrdMat* d_mats, const TrdJob* d_jobs, int njobs, int np_max, int grid, cudaStream_t s);
 int sytrd_max_grid();
+int sytrd_min_ctas(int n);
 
 // ---- divide and conquer (stedc.cu)
 struct DcMat {

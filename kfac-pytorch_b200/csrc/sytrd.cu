@@ -21,7 +21,7 @@ namespace kfac {
 
 namespace {
 
-constexpr int NB = TRD_NB, T = TRD_T, CP = TRD_CP;
+constexpr int NB = TRD_NB, T = TRD_T;
 constexpr int UPAD = T + 4;                 // row length of the transposed update staging
 constexpr int SUB_STAGE = 4 * NB * UPAD;    // floats per sub-group: VI^T, WI^T, VJ^T, WJ^T as [NB][UPAD]
 
@@ -56,130 +56,304 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-struct Ctx {
-  const TrdMat* m;
-  int cta, ncta;
-  // shared memory
-  float* vs;        // np
-  float* stage;     // 4 * SUB_STAGE  (update staging; phase A reuses it for the column partial sums)
-  float* red;       // 32 x 66 cross-warp reduction scratch
-  float* sc;        // scalars: [0,32) p1, [32,64) p2, 64 vAv, 65 sigma, 66 tau, 67 beta, 68 ytv, 69 w_{s+1}, 70 dnext
-  float* vrow;      // NB  V[s+1][:]
-  float* wrow;      // NB  W[s+1][:]
-};
+constexpr int MAXT = 256;                   // owned tiles per sub-group (list in shared memory)
+constexpr int NCP = 5;                      // ceil(max CTAs per group / 32)
 
-// x' for column c with P panel columns; also the diagonal d[c] and the |x'|^2 partial (rows >= c+2)
-__device__ void prep_column(const Ctx& cx, int c, int P) {
-  const TrdMat& mt = *cx.m;
-  const int n = mt.n, np = mt.np;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int GW = cx.ncta * 32, gw = cx.cta * 32 + warp;
-  float sig = 0.f;
-  int r0 = c + 1;
-  r0 += ((gw - r0) % GW + GW) % GW;        // first owned row >= c+1
-  for (int r = r0; r < n; r += GW) {
-    float t = 0.f;
-    if (lane < P) {
-      const float vr = __ldcg(&mt.Vp[(int64_t)r * NB + lane]);
-      const float wr = __ldcg(&mt.Wp[(int64_t)r * NB + lane]);
-      t = vr * cx.wrow[lane] + wr * cx.vrow[lane];
-    }
-    t = warp_sum(t);
-    if (lane == 0) {
-      const float x = __ldcg(&mt.A[(int64_t)r * np + c]) - t;
-      mt.col[r] = x;
-      if (r >= c + 2) sig = fmaf(x, x, sig);
-    }
+__device__ __forceinline__ float sum5(const float (&x)[NCP]) { return ((x[0] + x[1]) + (x[2] + x[3])) + x[4]; }
+
+// sums of 8 per-lane values over the warp with 9 shuffles: afterwards every lane holds the complete sum
+// of value number rowid(lane) = bit2 | bit3 << 1 | bit4 << 2 of its lane index
+__device__ __forceinline__ float reduce8(float (&r)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = (lane & 16) ? r[i + 4] : r[i], send = (lane & 16) ? r[i] : r[i + 4];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
   }
-  if (lane == 0) cx.red[warp] = sig;
-  __syncthreads();
-  if (warp == 0) {
-    float t = warp_sum(cx.red[lane]);
-    if (lane == 0) mt.cpart[cx.cta * CP + 65] = t;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = (lane & 8) ? r[i + 2] : r[i], send = (lane & 8) ? r[i] : r[i + 2];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
   }
-  if (cx.cta == 0 && warp == 1) {
-    float t = 0.f;
-    if (lane < P) t = cx.vrow[lane] * cx.wrow[lane];
-    t = warp_sum(t);
-    if (lane == 0) mt.d[c] = __ldcg(&mt.A[(int64_t)c * np + c]) - 2.f * t;
+  {
+    const float keep = (lane & 4) ? r[1] : r[0], send = (lane & 4) ? r[0] : r[1];
+    r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
   }
+  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 2);
+  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+  return r[0];
 }
 
+// One column costs two dependent L2 round trips and two group barriers: every phase first ISSUES all its global
+// loads (they are mutually independent), then computes.  cpart is stored transposed ([scalar][cta]) so that the
+// cross-CTA reductions read contiguous lines.
 __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem) {
   const int n = mt.n, np = mt.np, nblk = mt.nblk;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sg = warp >> 3, sw = warp & 7;           // sub-group (tile worker) and warp within it
   const int G = ncta * 4, sgid = cta * 4 + sg;       // tile owners
-  const int GW = ncta * 32, gw = cta * 32 + warp;    // row owners
-  Ctx cx;
-  cx.m = &mt; cx.cta = cta; cx.ncta = ncta;
-  cx.vs = smem;
-  cx.stage = cx.vs + np;
-  cx.red = cx.stage + 4 * SUB_STAGE;
-  cx.sc = cx.red + 32 * 66;
-  cx.vrow = cx.sc + 80;
-  cx.wrow = cx.vrow + NB;
+  const int GW = ncta * 32, gw = cta * 32 + warp;    // row owners: rows r = gw (mod GW)
+  float* stage = smem;                               // 4 * SUB_STAGE (update staging / column partial sums)
+  float* red = stage + 4 * SUB_STAGE;                // 32 x 66
+  float* sc = red + 32 * 66;                         // 80 scalars: [0,32) p1, [32,64) p2, 64 vAv
+  short2* tlist = reinterpret_cast<short2*>(sc + 80) + sg * MAXT;
+  __shared__ int s_ntile[4];
   unsigned epoch = 0;
+  float* const col = mt.col;
+  float* const cpart = mt.cpart;
+  const float* __restrict__ A = mt.A;
 
   if (n == 1) {
-    if (cta == 0 && tid == 0) { mt.d[0] = mt.A[0]; mt.tau[0] = 0.f; }
+    if (cta == 0 && tid == 0) { mt.d[0] = mt.A[0]; mt.tau[0] = 0.f; mt.e[0] = 0.f; }
     return;
   }
-  for (int i = tid; i < np; i += blockDim.x) cx.vs[i] = 0.f;
-  if (tid < NB) { cx.vrow[tid] = 0.f; cx.wrow[tid] = 0.f; }
+  // static tile ownership: tile (I, J), I >= J, belongs to sub-group (I (I + 1) / 2 + J) mod G
+  if ((tid & 255) == 0) {
+    int cnt = 0;
+    for (int I = 0; I < nblk; ++I) {
+      const int tri = (int)(((int64_t)I * (I + 1) / 2) % G);
+      for (int J = ((sgid - tri) % G + G) % G; J <= I; J += G)
+        if (cnt < MAXT) tlist[cnt++] = make_short2((short)I, (short)J);
+    }
+    s_ntile[sg] = cnt;
+  }
   __syncthreads();
-  int P = 0;                 // columns in the current panel
-  bool pending_update = false;
-  prep_column(cx, 0, 0);
+  const int ntile = s_ntile[sg];
+  int tfirst = 0;                                    // tiles before this index are dead (I < b0)
+
+  // ---- column 0: x = A[1:, 0], |x[1:]|^2 partials, d[0]
+  {
+    float sig = 0.f;
+    for (int r = gw; r < n; r += GW) {
+      if (r >= 1 && lane == 0) {
+        const float x = __ldcg(&A[(int64_t)r * np]);
+        col[r] = x;
+        if (r >= 2) sig = fmaf(x, x, sig);
+      }
+    }
+    if (lane == 0) red[warp] = sig;
+    __syncthreads();
+    if (warp == 0) {
+      const float t = warp_sum(red[lane]);
+      if (lane == 0) { cpart[65 * ncta + cta] = t; if (cta == 0) mt.d[0] = __ldcg(&A[0]); }
+    }
+  }
   group_barrier(mt.bar, epoch, ncta);
 
+  int P = 0;                                         // columns in the current panel
   for (int s = 0; s <= n - 2; ++s) {
-    // ------------------------------------------------------------ phase C: Householder vector of column s
-    if (warp == 0) {
-      float t = 0.f;
-      for (int c = lane; c < ncta; c += 32) t += __ldcg(&mt.cpart[c * CP + 65]);
-      t = warp_sum(t);
-      if (lane == 0) {
-        const float alpha = __ldcg(&mt.col[s + 1]);
-        float beta, tau, scal;
-        if (t == 0.f) { beta = alpha; tau = 0.f; scal = 0.f; }
-        else {
-          beta = -copysignf(sqrtf(fmaf(alpha, alpha, t)), alpha);
-          tau = (beta - alpha) / beta;
-          scal = 1.f / (alpha - beta);
-        }
-        cx.sc[66] = tau; cx.sc[67] = beta; cx.sc[71] = scal;
-        if (cta == 0) { mt.e[s] = beta; mt.tau[s] = tau; }
-      }
+    const int b0 = (s + 1) / T;
+    while (tfirst < ntile && tlist[tfirst].x < b0) ++tfirst;
+    // =========================================================== phase C + A
+    // Householder scalars (every warp redundantly: no block-level sync on the critical path)
+    float sgp[NCP];
+#pragma unroll
+    for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; sgp[j] = c < ncta ? __ldcg(&cpart[65 * ncta + c]) : 0.f; }
+    const float alpha = __ldcg(&col[s + 1]);
+    // own rows (batches of 4): raw v and the panel rows
+    auto raw_v = [&](int r) { return (r > s + 1 && r < n) ? __ldcg(&col[r]) : 0.f; };
+    const float sigma = warp_sum(sum5(sgp));
+    float beta, tau, scal;
+    if (sigma == 0.f) { beta = alpha; tau = 0.f; scal = 0.f; }
+    else {
+      beta = -copysignf(sqrtf(fmaf(alpha, alpha, sigma)), alpha);
+      tau = (beta - alpha) / beta;
+      scal = 1.f / (alpha - beta);
     }
-    __syncthreads();
-    {
-      const float scal = cx.sc[71];
-      for (int r = tid; r < np; r += blockDim.x) {
-        float v = 0.f;
-        if (r == s + 1) v = 1.f;
-        else if (r > s + 1 && r < n) v = __ldcg(&mt.col[r]) * scal;
-        cx.vs[r] = v;
-      }
-    }
-    __syncthreads();
+    auto vfix = [&](int r, float raw) { return r == s + 1 ? 1.f : raw * scal; };
+    if (cta == 0 && tid == 0) { mt.e[s] = beta; mt.tau[s] = tau; }
     // the Householder vector is kept for the back-transformation (each CTA writes a slice of the row)
     {
       const int per = (n + ncta - 1) / ncta;
       const int a = cta * per, b = min(n, a + per);
       float* vt = mt.VT + (int64_t)s * mt.ldv;
-      for (int r = a + tid; r < b; r += blockDim.x) vt[r] = cx.vs[r];
+      for (int r = a + tid; r < b; r += blockDim.x) vt[r] = vfix(r, raw_v(r));
     }
-    // ------------------------------------------------------------ pending rank-2NB update of the lower tiles
-    if (pending_update) {
-      const int b0 = (s + 1) / T;
-      float* st = cx.stage + sg * SUB_STAGE;
+    // symmetric product with the lower tiles of this sub-group
+    float vav = 0.f;
+    {
+      float* cs = stage + sg * (8 * T);              // column partial sums: [8 warps][64]
+      const int st_tid = tid & 255;
+      for (int ti = tfirst; ti < ntile; ++ti) {
+        const int I = tlist[ti].x, J = tlist[ti].y;
+        if (J < b0) continue;
+        const int rb = I * T + sw * 8, c0 = J * T + 2 * lane;
+        float2 a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(&A[(int64_t)(rb + k) * np + c0]));
+        const float rj0 = raw_v(c0), rj1 = raw_v(c0 + 1);
+        const float ri = raw_v(rb + (lane & 7));
+        const float vj0 = vfix(c0, rj0), vj1 = vfix(c0 + 1, rj1);
+        const float vi_l = vfix(rb + (lane & 7), ri);
+        float rs[8];
+        float c0acc = 0.f, c1acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float vi = __shfl_sync(0xffffffffu, vi_l, k);
+          rs[k] = fmaf(a[k].x, vj0, a[k].y * vj1);
+          c0acc = fmaf(a[k].x, vi, c0acc);
+          c1acc = fmaf(a[k].y, vi, c1acc);
+        }
+        const float tot = reduce8(rs, lane);
+        const int rid = ((lane >> 2) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 4) & 1) << 2);
+        const float vi_r = __shfl_sync(0xffffffffu, vi_l, rid);
+        if ((lane & 3) == 0) {
+          mt.part[(int64_t)J * np + rb + rid] = tot;
+          const float t = tot * vi_r;
+          vav += (I == J) ? t : 2.f * t;
+        }
+        if (I != J) {
+          sub_sync(sg);                              // previous tile's readers are done with cs
+          cs[sw * T + 2 * lane] = c0acc;
+          cs[sw * T + 2 * lane + 1] = c1acc;
+          sub_sync(sg);
+          if (st_tid < T) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += cs[w * T + st_tid];
+            mt.part[(int64_t)I * np + J * T + st_tid] = t;
+          }
+        }
+      }
+    }
+    // per-CTA partials of p1 = W^T v, p2 = V^T v (lane = panel column) over the owned rows
+    float p1 = 0.f, p2 = 0.f;
+    if (P > 0) {
+      int r0 = s + 1;
+      r0 += ((gw - r0) % GW + GW) % GW;
+      for (int rb4 = r0; rb4 < n; rb4 += 4 * GW) {
+        float rw[4], wv[4], vv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = rb4 + k * GW;
+          rw[k] = raw_v(r);
+          const bool ok = r < n && lane < P;
+          wv[k] = ok ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
+          vv[k] = ok ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float v = vfix(rb4 + k * GW, rw[k]);
+          p1 = fmaf(wv[k], v, p1);
+          p2 = fmaf(vv[k], v, p2);
+        }
+      }
+    }
+    vav = warp_sum(vav);
+    red[warp * 66 + lane] = p1;
+    red[warp * 66 + 32 + lane] = p2;
+    if (lane == 0) red[warp * 66 + 64] = vav;
+    __syncthreads();
+    if (tid < 65) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int w = 0; w < 32; ++w) t += red[w * 66 + tid];
+      cpart[tid * ncta + cta] = t;
+    }
+    group_barrier(mt.bar, epoch, ncta);
+    // =========================================================== phase B
+    {
+      // (a) cross-CTA sums of p1, p2, vAv: warp w owns outputs w, w + 32 and (warp 0) 64
+      float ca[NCP], cb[NCP], cc[NCP];
+      const bool need_a = warp < P, need_b = warp < P;          // outputs warp (p1) and 32 + warp (p2)
+#pragma unroll
+      for (int j = 0; j < NCP; ++j) {
+        const int c = lane + 32 * j;
+        const bool in = c < ncta;
+        ca[j] = (in && need_a) ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
+        cb[j] = (in && need_b) ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
+        cc[j] = (in && warp == 0) ? __ldcg(&cpart[64 * ncta + c]) : 0.f;
+      }
+      // (b) row s+1 (every warp redundantly): y, panel rows
+      const int r1 = s + 1;
+      float y1p[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; y1p[j] = X < nblk ? __ldcg(&mt.part[(int64_t)X * np + r1]) : 0.f; }
+      float vrow = (lane < P) ? __ldcg(&mt.Vp[(int64_t)r1 * NB + lane]) : 0.f;
+      float wrow = (lane < P) ? __ldcg(&mt.Wp[(int64_t)r1 * NB + lane]) : 0.f;
+      const float a11 = __ldcg(&A[(int64_t)r1 * np + r1]);
+      // (c) own rows, first batch of 4 (further batches pay another round trip)
+      int r0 = s + 1;
+      r0 += ((gw - r0) % GW + GW) % GW;
+      float yp[4][3], vr[4], wr[4], ar[4], rw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + k * GW;
+        const bool okr = r < n;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; yp[k][j] = (okr && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f; }
+        vr[k] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
+        wr[k] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
+        ar[k] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
+        rw[k] = raw_v(r);
+      }
+      // reduce (a) and publish through shared memory
+      const float sa = warp_sum(sum5(ca)), sb = warp_sum(sum5(cb)), scv = warp_sum(sum5(cc));
+      if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
+      __syncthreads();
+      const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
+      const float ytv = sc[64] - 2.f * warp_sum(p1l * p2l);
+      // row s+1
+      const float y1 = warp_sum((y1p[0] + y1p[1]) + y1p[2]) - warp_sum(vrow * p1l + wrow * p2l);
+      const float w1 = tau * (y1 - 0.5f * tau * ytv);            // v[s+1] = 1
+      if (lane == P) { vrow = 1.f; wrow = w1; }
+      {                                                          // the owner of row s+1 writes the diagonal
+        const float dd = warp_sum(vrow * wrow);
+        if (gw == (r1 % GW) && lane == 0) mt.d[r1] = a11 - 2.f * dd;
+      }
+      float sig = 0.f;
+      for (int rb4 = r0; rb4 < n; rb4 += 4 * GW) {
+        if (rb4 != r0) {                                         // later batches: load now
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = rb4 + k * GW;
+            const bool okr = r < n;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; yp[k][j] = (okr && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f; }
+            vr[k] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
+            wr[k] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
+            ar[k] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
+            rw[k] = raw_v(r);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = rb4 + k * GW;
+          if (r >= n) continue;                                  // warp-uniform
+          const float v = vfix(r, rw[k]);
+          const float y = warp_sum((yp[k][0] + yp[k][1]) + yp[k][2]) - warp_sum(vr[k] * p1l + wr[k] * p2l);
+          const float w = tau * (y - 0.5f * tau * ytv * v);
+          if (lane == 0) {
+            mt.Wp[(int64_t)r * NB + P] = w;
+            mt.Vp[(int64_t)r * NB + P] = v;
+          }
+          // next effective column x' = A[:, s+1] - V W[s+1,:]^T - W V[s+1,:]^T  (panel incl. the new column P)
+          const float vl = (lane == P) ? v : vr[k], wl = (lane == P) ? w : wr[k];
+          const float t = warp_sum(vl * wrow + wl * vrow);
+          if (r >= s + 2 && lane == 0) {
+            const float x = ar[k] - t;
+            col[r] = x;
+            if (r >= s + 3) sig = fmaf(x, x, sig);
+          }
+        }
+      }
+      if (lane == 0) red[warp] = sig;
+      __syncthreads();
+      if (warp == 0) {
+        const float t = warp_sum(red[lane]);
+        if (lane == 0) cpart[65 * ncta + cta] = t;
+      }
+      P += 1;
+    }
+    group_barrier(mt.bar, epoch, ncta);
+    // =========================================================== rank-2NB update of the lower tiles
+    if (P == NB && s < n - 2) {
+      const int ub0 = (s + 2) / T;
+      float* st = stage + sg * SUB_STAGE;
       float* VIt = st, *WIt = st + NB * UPAD, *VJt = st + 2 * NB * UPAD, *WJt = st + 3 * NB * UPAD;
       const int st_tid = tid & 255;
-      for (int I = b0; I < nblk; ++I) {
-        const int tri = (int)(((int64_t)I * (I + 1) / 2) % G);
-        for (int J = ((sgid - tri) % G + G) % G; J <= I; J += G) {     // uniform within the sub-group
-        if (J < b0) continue;
+      for (int ti = tfirst; ti < ntile; ++ti) {
+        const int I = tlist[ti].x, J = tlist[ti].y;
+        if (I < ub0 || J < ub0) continue;            // uniform within the sub-group
         sub_sync(sg);
         // stage the four 64 x NB operand blocks transposed ([k][row])
 #pragma unroll
@@ -222,138 +396,10 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
           a.x -= acc[i][0]; a.y -= acc[i][1]; a.z -= acc[i][2]; a.w -= acc[i][3];
           *p = a;
         }
-        }
       }
-      pending_update = false;
       P = 0;
       group_barrier(mt.bar, epoch, ncta);
     }
-    // ------------------------------------------------------------ phase A: symmetric product, lower tiles
-    {
-      const int b0 = (s + 1) / T;
-      float vav = 0.f;
-      float* cs = cx.stage + sg * (8 * T);          // column partial sums of this sub-group: [8 warps][64]
-      for (int I = b0; I < nblk; ++I) {
-        const int tri = (int)(((int64_t)I * (I + 1) / 2) % G);
-        for (int J = ((sgid - tri) % G + G) % G; J <= I; J += G) {
-        if (J < b0) continue;
-        const int rb = I * T + sw * 8, c0 = J * T + 2 * lane;
-        float2 a[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(&mt.A[(int64_t)(rb + k) * np + c0]));
-        const float vj0 = cx.vs[c0], vj1 = cx.vs[c0 + 1];
-        float c0acc = 0.f, c1acc = 0.f, vloc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float vi = cx.vs[rb + k];
-          float rs = fmaf(a[k].x, vj0, a[k].y * vj1);
-          c0acc = fmaf(a[k].x, vi, c0acc);
-          c1acc = fmaf(a[k].y, vi, c1acc);
-          rs = warp_sum(rs);
-          if (lane == 0) {
-            mt.part[(int64_t)J * np + rb + k] = rs;
-            vloc = fmaf(rs, vi, vloc);
-          }
-        }
-        vav += (I == J) ? vloc : 2.f * vloc;
-        if (I != J) {
-          sub_sync(sg);                       // previous tile's readers are done with cs
-          cs[sw * T + 2 * lane] = c0acc;
-          cs[sw * T + 2 * lane + 1] = c1acc;
-          sub_sync(sg);
-          const int st_tid = tid & 255;
-          if (st_tid < T) {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) t += cs[w * T + st_tid];
-            mt.part[(int64_t)I * np + J * T + st_tid] = t;
-          }
-        }
-        }
-      }
-      // per-CTA partials of p1 = W^T v, p2 = V^T v (lane = panel column) over the owned rows
-      float p1 = 0.f, p2 = 0.f;
-      if (P > 0) {
-        int r0 = s + 1;
-        r0 += ((gw - r0) % GW + GW) % GW;
-        for (int r = r0; r < n; r += GW) {
-          if (lane < P) {
-            const float v = cx.vs[r];
-            p1 = fmaf(__ldcg(&mt.Wp[(int64_t)r * NB + lane]), v, p1);
-            p2 = fmaf(__ldcg(&mt.Vp[(int64_t)r * NB + lane]), v, p2);
-          }
-        }
-      }
-      __syncthreads();                        // all sub-groups are done with `stage`
-      cx.red[warp * 66 + lane] = p1;
-      cx.red[warp * 66 + 32 + lane] = p2;
-      if (lane == 0) cx.red[warp * 66 + 64] = vav;
-      __syncthreads();
-      if (tid < 65) {
-        float t = 0.f;
-#pragma unroll 8
-        for (int w = 0; w < 32; ++w) t += cx.red[w * 66 + tid];
-        mt.cpart[cta * CP + tid] = t;
-      }
-    }
-    group_barrier(mt.bar, epoch, ncta);
-    // ------------------------------------------------------------ phase B: w column, next effective column
-    {
-      // reduce the per-CTA partials (outputs 0..64), every CTA redundantly
-      for (int o = warp; o < 65; o += 32) {
-        float t = 0.f;
-        const bool need = (o == 64) || ((o & 31) < P);
-        if (need)
-          for (int c = lane; c < ncta; c += 32) t += __ldcg(&mt.cpart[c * CP + o]);
-        t = warp_sum(t);
-        if (lane == 0) cx.sc[o] = t;
-      }
-      __syncthreads();
-      const float tau = cx.sc[66];
-      const int b0 = (s + 1) / T;
-      if (warp == 0) {
-        float t = (lane < P) ? cx.sc[lane] * cx.sc[32 + lane] : 0.f;
-        t = warp_sum(t);
-        const float ytv = cx.sc[64] - 2.f * t;
-        // row s+1: y, w and the panel rows V[s+1][:], W[s+1][:]
-        const int r = s + 1;
-        float yr = 0.f;
-        for (int X = b0 + lane; X < nblk; X += 32) yr += __ldcg(&mt.part[(int64_t)X * np + r]);
-        float vr = 0.f, wr = 0.f, corr = 0.f;
-        if (lane < P) {
-          vr = __ldcg(&mt.Vp[(int64_t)r * NB + lane]);
-          wr = __ldcg(&mt.Wp[(int64_t)r * NB + lane]);
-          corr = vr * cx.sc[lane] + wr * cx.sc[32 + lane];
-        }
-        yr = warp_sum(yr) - warp_sum(corr);
-        const float w1 = tau * (yr - 0.5f * tau * ytv);          // v[s+1] = 1
-        if (lane == P) { vr = 1.f; wr = w1; }
-        cx.vrow[lane] = vr; cx.wrow[lane] = wr;
-        if (lane == 0) cx.sc[68] = ytv;
-      }
-      __syncthreads();
-      const float ytv = cx.sc[68];
-      int r0 = s + 1;
-      r0 += ((gw - r0) % GW + GW) % GW;
-      for (int r = r0; r < n; r += GW) {
-        float yr = 0.f;
-        for (int X = b0 + lane; X < nblk; X += 32) yr += __ldcg(&mt.part[(int64_t)X * np + r]);
-        float corr = 0.f;
-        if (lane < P)
-          corr = __ldcg(&mt.Vp[(int64_t)r * NB + lane]) * cx.sc[lane] + __ldcg(&mt.Wp[(int64_t)r * NB + lane]) * cx.sc[32 + lane];
-        yr = warp_sum(yr) - warp_sum(corr);
-        if (lane == 0) {
-          const float v = cx.vs[r];
-          mt.Wp[(int64_t)r * NB + P] = tau * (yr - 0.5f * tau * ytv * v);
-          mt.Vp[(int64_t)r * NB + P] = v;
-        }
-      }
-      __syncthreads();        // own rows' panel column P is written (re-read below by the same warps)
-      prep_column(cx, s + 1, P + 1);
-      P += 1;
-      if (P == NB) pending_update = true;
-    }
-    group_barrier(mt.bar, epoch, ncta);
   }
   if (cta == 0 && tid == 0) { mt.e[n - 1] = 0.f; mt.tau[n - 1] = 0.f; }
 }
@@ -369,13 +415,22 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) sytrd_kernel(const TrdMat* mat
   }
 }
 
-size_t trd_smem_bytes(int np_max) {
-  return sizeof(float) * ((size_t)np_max + 4 * SUB_STAGE + 32 * 66 + 80 + 2 * NB + 16);
+size_t trd_smem_bytes(int) {
+  return sizeof(float) * ((size_t)4 * SUB_STAGE + 32 * 66 + 80) + sizeof(short2) * 4 * MAXT + 64;
 }
 
 }  // namespace
 
 int sytrd_max_grid() { return tc_num_sms(); }
+
+// smallest group that can own all lower tiles of an n x n matrix (tile list of MAXT entries per sub-group)
+int sytrd_min_ctas(int n) {
+  const int nblk = (n + T - 1) / T, tiles = nblk * (nblk + 1) / 2;
+  if (nblk >= MAXT) return 1 << 30;
+  int C = 1;
+  while (tiles / (4 * C) + nblk + 1 > MAXT) ++C;
+  return C;
+}
 
 int launch_sytrd(const TrdMat* d_mats, const TrdJob* d_jobs, int njobs, int np_max, int grid, cudaStream_t s) {
   if (njobs <= 0) return KFAC_OK;

@@ -65,7 +65,7 @@ def run_sytrd(lib, F, ncta):
 @pytest.mark.parametrize('n,ncta,kind', [(2, 1, 'rand'), (3, 1, 'rand'), (33, 1, 'rand'), (64, 2, 'rand'), (65, 3, 'rand'),
                                          (130, 1, 'rand'), (200, 7, 'kfac'), (257, 5, 'rand'), (576, 0, 'kfac'),
                                          (1000, 0, 'rand'), (1024, 12, 'kfac'), (777, 148, 'diag'), (2049, 0, 'kfac'),
-                                         (4608, 0, 'kfac')])
+                                         (2304, 24, 'kfac'), (4608, 36, 'kfac'), (4608, 74, 'kfac'), (4608, 0, 'kfac')])
 def test_sytrd(lib, n, ncta, kind):
     F = sym(n, n, kind)
     d, e, tau, VT, ms = run_sytrd(lib, F, ncta)
