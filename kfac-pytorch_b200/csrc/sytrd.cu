@@ -35,12 +35,12 @@ __device__ __forceinline__ void group_barrier(unsigned* bar, unsigned& epoch, in
   __syncthreads();
   if (ncta > 1) {
     if (threadIdx.x == 0) {
-      __threadfence();
+      // release-increment / acquire-poll: bar.sync made the CTA's writes visible to this thread (cta scope),
+      // the gpu-scope release is cumulative; no separate MEMBARs on the critical path
       epoch += 1;
-      atomicAdd(bar, 1u);
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
       const unsigned target = epoch * (unsigned)ncta;
       while (ld_acquire(bar) < target) {}
-      __threadfence();
     }
     __syncthreads();
   }
@@ -94,8 +94,8 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   const int GW = ncta * 32, gw = cta * 32 + warp;    // row owners: rows r = gw (mod GW)
   float* stage = smem;                               // 4 * SUB_STAGE (update staging / column partial sums)
   float* red = stage + 4 * SUB_STAGE;                // 32 x 66
-  float* sc = red + 32 * 66;                         // 80 scalars: [0,32) p1, [32,64) p2, 64 vAv
-  short2* tlist = reinterpret_cast<short2*>(sc + 80) + sg * MAXT;
+  float* sc = red + 32 * 66;                         // 160 scalars: [0,32) p1, [32,64) p2, 64 vAv, 66.. misc, [96,128) vrow, [128,160) wrow
+  short2* tlist = reinterpret_cast<short2*>(sc + 160) + sg * MAXT;
   __shared__ int s_ntile[4];
   unsigned epoch = 0;
   float* const col = mt.col;
@@ -140,27 +140,40 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   group_barrier(mt.bar, epoch, ncta);
 
   int P = 0;                                         // columns in the current panel
+  // Vector work is organised in ROW BLOCKS of 32 consecutive rows: block k belongs to CTA (k mod ncta), warp
+  // ((k / ncta) mod 32).  A warp works on a block either with lane = panel column (dots) or lane = row (everything
+  // else), so the per-row instruction count is ~5-10 instead of one warp reduction per row and per quantity.
+  const int nrb = (n + 31) / 32;
+  float* s_vrow = sc + 96;                           // 32: V[s+1][:]
+  float* s_wrow = sc + 128;                          // 32: W[s+1][:]
   for (int s = 0; s <= n - 2; ++s) {
     const int b0 = (s + 1) / T;
+    const int rb_first = (s + 1) / 32;               // first row block with an active row
     while (tfirst < ntile && tlist[tfirst].x < b0) ++tfirst;
-    // =========================================================== phase C + A
-    // Householder scalars (every warp redundantly: no block-level sync on the critical path)
-    float sgp[NCP];
+    // =========================================================== phase C: Householder scalars (warp 0)
+    if (warp == 0) {
+      float sgp[NCP];
 #pragma unroll
-    for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; sgp[j] = c < ncta ? __ldcg(&cpart[65 * ncta + c]) : 0.f; }
-    const float alpha = __ldcg(&col[s + 1]);
-    // own rows (batches of 4): raw v and the panel rows
-    auto raw_v = [&](int r) { return (r > s + 1 && r < n) ? __ldcg(&col[r]) : 0.f; };
-    const float sigma = warp_sum(sum5(sgp));
-    float beta, tau, scal;
-    if (sigma == 0.f) { beta = alpha; tau = 0.f; scal = 0.f; }
-    else {
-      beta = -copysignf(sqrtf(fmaf(alpha, alpha, sigma)), alpha);
-      tau = (beta - alpha) / beta;
-      scal = 1.f / (alpha - beta);
+      for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; sgp[j] = c < ncta ? __ldcg(&cpart[65 * ncta + c]) : 0.f; }
+      const float alpha = __ldcg(&col[s + 1]);
+      const float sigma = warp_sum(sum5(sgp));
+      if (lane == 0) {
+        float beta, tau, scal;
+        if (sigma == 0.f) { beta = alpha; tau = 0.f; scal = 0.f; }
+        else {
+          beta = -copysignf(sqrtf(fmaf(alpha, alpha, sigma)), alpha);
+          tau = (beta - alpha) / beta;
+          scal = 1.f / (alpha - beta);
+        }
+        sc[66] = tau; sc[67] = scal;
+        if (cta == 0) { mt.e[s] = beta; mt.tau[s] = tau; }
+      }
     }
+    __syncthreads();
+    const float tau = sc[66], scal = sc[67];
+    auto raw_v = [&](int r) { return (r > s + 1 && r < n) ? __ldcg(&col[r]) : 0.f; };
     auto vfix = [&](int r, float raw) { return r == s + 1 ? 1.f : raw * scal; };
-    if (cta == 0 && tid == 0) { mt.e[s] = beta; mt.tau[s] = tau; }
+    // =========================================================== phase A
     // the Householder vector is kept for the back-transformation (each CTA writes a slice of the row)
     {
       const int per = (n + ncta - 1) / ncta;
@@ -215,26 +228,21 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         }
       }
     }
-    // per-CTA partials of p1 = W^T v, p2 = V^T v (lane = panel column) over the owned rows
+    // per-CTA partials of p1 = W^T v, p2 = V^T v over the owned row blocks (lane = panel column)
     float p1 = 0.f, p2 = 0.f;
     if (P > 0) {
-      int r0 = s + 1;
-      r0 += ((gw - r0) % GW + GW) % GW;
-      for (int rb4 = r0; rb4 < n; rb4 += 4 * GW) {
-        float rw[4], wv[4], vv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = rb4 + k * GW;
-          rw[k] = raw_v(r);
-          const bool ok = r < n && lane < P;
-          wv[k] = ok ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
-          vv[k] = ok ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float v = vfix(rb4 + k * GW, rw[k]);
-          p1 = fmaf(wv[k], v, p1);
-          p2 = fmaf(vv[k], v, p2);
+      for (int k = cta + ncta * warp; k < nrb; k += ncta * 32) {
+        if (k < rb_first) continue;
+        const int rbase = k * 32;
+        const float vl = vfix(rbase + lane, raw_v(rbase + lane));      // lane j holds v[rbase + j]
+        const int rend = min(32, n - rbase);
+#pragma unroll 4
+        for (int j = 0; j < rend; ++j) {
+          const float v = __shfl_sync(0xffffffffu, vl, j);
+          if (lane < P) {
+            p1 = fmaf(__ldcg(&mt.Wp[(int64_t)(rbase + j) * NB + lane]), v, p1);
+            p2 = fmaf(__ldcg(&mt.Vp[(int64_t)(rbase + j) * NB + lane]), v, p2);
+          }
         }
       }
     }
@@ -252,90 +260,88 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     group_barrier(mt.bar, epoch, ncta);
     // =========================================================== phase B
     {
-      // (a) cross-CTA sums of p1, p2, vAv: warp w owns outputs w, w + 32 and (warp 0) 64
-      float ca[NCP], cb[NCP], cc[NCP];
-      const bool need_a = warp < P, need_b = warp < P;          // outputs warp (p1) and 32 + warp (p2)
+      // cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
+      {
+        float ca[NCP], cb[NCP], cc[NCP];
+        const bool need = warp < P;
 #pragma unroll
-      for (int j = 0; j < NCP; ++j) {
-        const int c = lane + 32 * j;
-        const bool in = c < ncta;
-        ca[j] = (in && need_a) ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
-        cb[j] = (in && need_b) ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
-        cc[j] = (in && warp == 0) ? __ldcg(&cpart[64 * ncta + c]) : 0.f;
+        for (int j = 0; j < NCP; ++j) {
+          const int c = lane + 32 * j;
+          const bool in = c < ncta;
+          ca[j] = (in && need) ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
+          cb[j] = (in && need) ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
+          cc[j] = (in && warp == 0) ? __ldcg(&cpart[64 * ncta + c]) : 0.f;
+        }
+        if (need || warp == 0) {
+          const float sa = warp_sum(sum5(ca)), sb = warp_sum(sum5(cb));
+          if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; }
+          if (warp == 0) { const float scv = warp_sum(sum5(cc)); if (lane == 0) sc[64] = scv; }
+        } else if (lane == 0) { sc[warp] = 0.f; sc[32 + warp] = 0.f; }
       }
-      // (b) row s+1 (every warp redundantly): y, panel rows
+      // row s+1 (warp 1): raw loads now, the rest after the sums are published
       const int r1 = s + 1;
-      float y1p[3];
+      float y1p[3] = {0.f, 0.f, 0.f}, vrow = 0.f, wrow = 0.f, a11 = 0.f;
+      if (warp == 1) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; y1p[j] = X < nblk ? __ldcg(&mt.part[(int64_t)X * np + r1]) : 0.f; }
-      float vrow = (lane < P) ? __ldcg(&mt.Vp[(int64_t)r1 * NB + lane]) : 0.f;
-      float wrow = (lane < P) ? __ldcg(&mt.Wp[(int64_t)r1 * NB + lane]) : 0.f;
-      const float a11 = __ldcg(&A[(int64_t)r1 * np + r1]);
-      // (c) own rows, first batch of 4 (further batches pay another round trip)
-      int r0 = s + 1;
-      r0 += ((gw - r0) % GW + GW) % GW;
-      float yp[4][3], vr[4], wr[4], ar[4], rw[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = r0 + k * GW;
-        const bool okr = r < n;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; yp[k][j] = (okr && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f; }
-        vr[k] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
-        wr[k] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
-        ar[k] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
-        rw[k] = raw_v(r);
+        for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; y1p[j] = X < nblk ? __ldcg(&mt.part[(int64_t)X * np + r1]) : 0.f; }
+        vrow = (lane < P) ? __ldcg(&mt.Vp[(int64_t)r1 * NB + lane]) : 0.f;
+        wrow = (lane < P) ? __ldcg(&mt.Wp[(int64_t)r1 * NB + lane]) : 0.f;
+        a11 = __ldcg(&A[(int64_t)r1 * np + r1]);
       }
-      // reduce (a) and publish through shared memory
-      const float sa = warp_sum(sum5(ca)), sb = warp_sum(sum5(cb)), scv = warp_sum(sum5(cc));
-      if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
       __syncthreads();
-      const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
-      const float ytv = sc[64] - 2.f * warp_sum(p1l * p2l);
-      // row s+1
-      const float y1 = warp_sum((y1p[0] + y1p[1]) + y1p[2]) - warp_sum(vrow * p1l + wrow * p2l);
-      const float w1 = tau * (y1 - 0.5f * tau * ytv);            // v[s+1] = 1
-      if (lane == P) { vrow = 1.f; wrow = w1; }
-      {                                                          // the owner of row s+1 writes the diagonal
+      if (warp == 1) {
+        const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
+        const float ytv = sc[64] - 2.f * warp_sum(p1l * p2l);
+        const float y1 = warp_sum((y1p[0] + y1p[1]) + y1p[2] - (vrow * p1l + wrow * p2l));
+        const float w1 = tau * (y1 - 0.5f * tau * ytv);            // v[s+1] = 1
+        if (lane == P) { vrow = 1.f; wrow = w1; }
+        s_vrow[lane] = vrow; s_wrow[lane] = wrow;
         const float dd = warp_sum(vrow * wrow);
-        if (gw == (r1 % GW) && lane == 0) mt.d[r1] = a11 - 2.f * dd;
+        if (lane == 0) { sc[68] = ytv; sc[69] = w1; if (cta == 0) mt.d[r1] = a11 - 2.f * dd; }
       }
+      __syncthreads();
+      const float ytv = sc[68], w1 = sc[69];
+      // own row blocks, lane = row: y = A v - V p1 - W p2, w, next effective column x'
       float sig = 0.f;
-      for (int rb4 = r0; rb4 < n; rb4 += 4 * GW) {
-        if (rb4 != r0) {                                         // later batches: load now
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int r = rb4 + k * GW;
-            const bool okr = r < n;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; yp[k][j] = (okr && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f; }
-            vr[k] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
-            wr[k] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
-            ar[k] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
-            rw[k] = raw_v(r);
+      for (int k = cta + ncta * warp; k < nrb; k += ncta * 32) {
+        if (k < rb_first) continue;
+        const int r = k * 32 + lane;
+        const bool act = r >= s + 1 && r < n;
+        float y = 0.f;
+        if (act)
+          for (int X = b0; X < nblk; ++X) y += __ldcg(&mt.part[(int64_t)X * np + r]);
+        const float v = act ? vfix(r, raw_v(r)) : 0.f;
+        const float acol = (act && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
+        float corr = 0.f, xs = 0.f;
+        if (act) {
+          const float4* vp = reinterpret_cast<const float4*>(&mt.Vp[(int64_t)r * NB]);
+          const float4* wp = reinterpret_cast<const float4*>(&mt.Wp[(int64_t)r * NB]);
+          for (int i4 = 0; i4 * 4 < P; ++i4) {
+            const float4 vv = __ldcg(vp + i4), ww = __ldcg(wp + i4);
+            const float4 q1 = *reinterpret_cast<const float4*>(&sc[i4 * 4]), q2 = *reinterpret_cast<const float4*>(&sc[32 + i4 * 4]);
+            const float4 vr4 = *reinterpret_cast<const float4*>(&s_vrow[i4 * 4]), wr4 = *reinterpret_cast<const float4*>(&s_wrow[i4 * 4]);
+            // entries i >= P of the panel row are stale: mask them (sc / s_vrow / s_wrow are zero there except column P)
+            const float m0 = (i4 * 4 + 0 < P) ? 1.f : 0.f, m1 = (i4 * 4 + 1 < P) ? 1.f : 0.f, m2 = (i4 * 4 + 2 < P) ? 1.f : 0.f,
+                        m3 = (i4 * 4 + 3 < P) ? 1.f : 0.f;
+            corr += m0 * (vv.x * q1.x + ww.x * q2.x) + m1 * (vv.y * q1.y + ww.y * q2.y) + m2 * (vv.z * q1.z + ww.z * q2.z) +
+                    m3 * (vv.w * q1.w + ww.w * q2.w);
+            xs += m0 * (vv.x * wr4.x + ww.x * vr4.x) + m1 * (vv.y * wr4.y + ww.y * vr4.y) + m2 * (vv.z * wr4.z + ww.z * vr4.z) +
+                  m3 * (vv.w * wr4.w + ww.w * vr4.w);
           }
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int r = rb4 + k * GW;
-          if (r >= n) continue;                                  // warp-uniform
-          const float v = vfix(r, rw[k]);
-          const float y = warp_sum((yp[k][0] + yp[k][1]) + yp[k][2]) - warp_sum(vr[k] * p1l + wr[k] * p2l);
+        if (act) {
+          y -= corr;
           const float w = tau * (y - 0.5f * tau * ytv * v);
-          if (lane == 0) {
-            mt.Wp[(int64_t)r * NB + P] = w;
-            mt.Vp[(int64_t)r * NB + P] = v;
-          }
-          // next effective column x' = A[:, s+1] - V W[s+1,:]^T - W V[s+1,:]^T  (panel incl. the new column P)
-          const float vl = (lane == P) ? v : vr[k], wl = (lane == P) ? w : wr[k];
-          const float t = warp_sum(vl * wrow + wl * vrow);
-          if (r >= s + 2 && lane == 0) {
-            const float x = ar[k] - t;
+          mt.Wp[(int64_t)r * NB + P] = w;
+          mt.Vp[(int64_t)r * NB + P] = v;
+          if (r >= s + 2) {
+            const float x = acol - xs - (v * w1 + w);            // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
             col[r] = x;
             if (r >= s + 3) sig = fmaf(x, x, sig);
           }
         }
       }
+      sig = warp_sum(sig);
       if (lane == 0) red[warp] = sig;
       __syncthreads();
       if (warp == 0) {
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) sytrd_kernel(const TrdMat* mat
 }
 
 size_t trd_smem_bytes(int) {
-  return sizeof(float) * ((size_t)4 * SUB_STAGE + 32 * 66 + 80) + sizeof(short2) * 4 * MAXT + 64;
+  return sizeof(float) * ((size_t)4 * SUB_STAGE + 32 * 66 + 160) + sizeof(short2) * 4 * MAXT + 64;
 }
 
 }  // namespace
