@@ -81,12 +81,13 @@ __global__ void clamp_copy_kernel(const float* src, float* dst, int n) {
 
 struct MatLayout {
   int n, np, nblk, nbt;
-  size_t A, VT, Q0, Q1, Vp, Wp, part, col, tau, d, e, cpart, bar, fscr, iscr, S, Tm;
+  size_t A, VT, Vb, Q0, Q1, Vp, Wp, part, col, tau, d, e, cpart, bar, fscr, iscr, S, Tm, Y, Y2, slabY, slabS;
+  int ksplit;      // split count of the longest reduction of the back-transformation (K = np)
 };
 
 struct Layout {
   std::vector<MatLayout> m;
-  size_t off_trd, off_jobs, off_dc, off_blocks, off_plan, plan_bytes, total;
+  size_t off_trd, off_jobs, off_dc, off_blocks, off_plan, plan_bytes, off_gws, gws_bytes, total;
   int nblocks;
 };
 
@@ -102,12 +103,18 @@ void make_layout(const int* n, int count, Layout& L) {
   L.off_blocks = take(sizeof(BtBlock) * std::max(1, L.nblocks));
   L.plan_bytes = stedc_plan_bytes(n, count);
   L.off_plan = take(L.plan_bytes);
+  L.gws_bytes = grouped_gemm_ws_bytes(std::max(L.nblocks, count));
+  L.off_gws = take(L.gws_bytes);
   const int grid = sytrd_max_grid();
   for (int i = 0; i < count; ++i) {
     MatLayout& m = L.m[i];
     m.n = n[i]; m.np = round_up(n[i], TRD_T); m.nblk = m.np / TRD_T; m.nbt = ceil_div(n[i], BT);
     const size_t sq = (size_t)m.np * m.np * sizeof(float);
-    m.A = take(sq + (size_t)m.np * BT * 4); m.VT = take(sq); m.Q0 = take(sq); m.Q1 = take(sq);
+    m.A = take(sq + (size_t)m.np * BT * 4); m.VT = take(sq); m.Vb = take(sq + (size_t)m.np * BT * 4); m.Q0 = take(sq); m.Q1 = take(sq);
+    m.ksplit = m.np > 1024 ? ceil_div(m.np, 512) : 1;
+    m.Y = take((size_t)m.np * BT * 4); m.Y2 = take((size_t)m.np * BT * 4);
+    m.slabY = take((size_t)m.ksplit * m.np * BT * 4);
+    m.slabS = take((size_t)m.nbt * m.ksplit * BT * BT * 4);
     m.Vp = take((size_t)m.np * TRD_NB * 4); m.Wp = take((size_t)m.np * TRD_NB * 4);
     m.part = take((size_t)m.nblk * m.np * 4);
     m.col = take((size_t)m.np * 4); m.tau = take((size_t)m.np * 4); m.d = take((size_t)m.np * 4); m.e = take((size_t)m.np * 4);
@@ -232,7 +239,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
   for (int i = 0; i < count; ++i) {
     const MatLayout& m = L.m[i];
     TrdMat& t = trd[i];
-    t.A = (float*)(base + m.A); t.VT = (float*)(base + m.VT); t.tau = (float*)(base + m.tau);
+    t.A = (float*)(base + m.A); t.VT = (float*)(base + m.VT); t.Vb = (float*)(base + m.Vb); t.tau = (float*)(base + m.tau);
     t.d = (float*)(base + m.d); t.e = (float*)(base + m.e);
     t.Vp = (float*)(base + m.Vp); t.Wp = (float*)(base + m.Wp); t.part = (float*)(base + m.part);
     t.col = (float*)(base + m.col); t.cpart = (float*)(base + m.cpart); t.bar = (unsigned int*)(base + m.bar);
@@ -247,6 +254,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)m.np * m.np, 256)), 256, 0, s>>>(items[i].F, m.n, t.A, m.np);
     KFAC_LAUNCH_CHECK();
     KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)m.np * m.np * 4, s));
+    KFAC_CUDA(cudaMemsetAsync(t.Vb, 0, (size_t)m.np * (m.np + BT) * 4, s));
     KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)m.np * TRD_NB * 4, s));
     KFAC_CUDA(cudaMemsetAsync(t.Wp, 0, (size_t)m.np * TRD_NB * 4, s));
     KFAC_CUDA(cudaMemsetAsync(t.bar, 0, 256, s));
@@ -275,59 +283,81 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
   }
   BtBlock* d_blocks = (BtBlock*)(base + L.off_blocks);
   KFAC_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(BtBlock) * blocks.size(), cudaMemcpyHostToDevice, s));
-  for (int i = 0; i < count; ++i) {
-    const MatLayout& m = L.m[i];
-    const TrdMat& t = trd[i];
-    for (int kb = 0; kb < m.nbt; ++kb) {
-      const int j0 = kb * BT, nb = std::min(BT, m.n - j0);
-      float* S = (float*)(base + m.S) + (size_t)kb * BT * BT;
-      // S = V_k^T V_k over the rows >= j0 (the vectors are zero above)
-      if ((rc = gemm_tn_plain(t.VT + (size_t)j0 * t.ldv + j0, t.ldv, t.VT + (size_t)j0 * t.ldv + j0, t.ldv, S, BT, nb, nb,
-                              m.np - j0, s)))
-        return rc;
+  void* gws = base + L.off_gws;
+  auto plain = [](const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N, int K) {
+    GroupedGemm g{};
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.D = D; g.ldd = ldd; g.M = M; g.N = N; g.K = K;
+    g.alpha = 1.f; g.epi = EPI_NONE; g.splits = 1; g.mode = 0;
+    return g;
+  };
+  // S_k = V_k^T V_k for every block of every matrix: one grouped launch (long reductions through slabs)
+  {
+    std::vector<GroupedGemm> gg;
+    for (int i = 0; i < count; ++i) {
+      const MatLayout& m = L.m[i];
+      const TrdMat& t = trd[i];
+      for (int kb = 0; kb < m.nbt; ++kb) {
+        const int j0 = kb * BT, nb = std::min(BT, m.n - j0), K = m.np - j0;
+        const float* Vk = t.VT + (size_t)j0 * t.ldv + j0;
+        GroupedGemm g = plain(Vk, t.ldv, Vk, t.ldv, (float*)(base + m.S) + (size_t)kb * BT * BT, BT, nb, nb, K);
+        if (K > 1024 && grouped_gemm_tc_ok(g)) {
+          g.splits = ceil_div(K, 512);
+          g.slab = (float*)(base + m.slabS) + (size_t)kb * m.ksplit * BT * BT; g.slab_stride = (int64_t)nb * BT;
+        }
+        gg.push_back(g);
+      }
     }
+    if ((rc = launch_grouped_gemm(gg.data(), (int)gg.size(), gws, L.gws_bytes, s))) return rc;
   }
   {
     static bool attr = false;
     const int lsmem = BT * (BT + 1) * (int)sizeof(float);
     if (!attr) { KFAC_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lsmem)); attr = true; }
     larft_kernel<<<(int)blocks.size(), BT, lsmem, s>>>(d_blocks);
+    KFAC_LAUNCH_CHECK();
   }
-  KFAC_LAUNCH_CHECK();
-  // the chains of different matrices are independent: spread them over the side streams
-  StreamPool& pool = stream_pool();
-  const bool spread = count > 1;
-  if (spread && (rc = pool.fork(s))) return rc;
-  const cudaStream_t s_main = s;
+  int max_nbt = 0;
   for (int i = 0; i < count; ++i) {
     const MatLayout& m = L.m[i];
-    const TrdMat& t = trd[i];
+    const DcMat& d = dc[i];
+    max_nbt = std::max(max_nbt, m.nbt);
+    transpose_ld_kernel<<<dim3(ceil_div(m.n, 32), ceil_div(m.n, 32)), dim3(32, 8), 0, s>>>(d.Q[d.result_buf], m.np,
+                                                                                          d.Q[d.result_buf ^ 1], m.np, m.n, m.n);
+    KFAC_LAUNCH_CHECK();
+  }
+  // block reflectors, last block first; step t handles block (nbt - 1 - t) of every matrix that still has one:
+  // three grouped launches per step instead of three GEMMs per block and matrix
+  for (int tstep = 0; tstep < max_nbt; ++tstep) {
+    std::vector<GroupedGemm> g1, g2, g3;
+    for (int i = 0; i < count; ++i) {
+      const MatLayout& m = L.m[i];
+      if (m.nbt <= tstep) continue;
+      const TrdMat& t = trd[i];
+      const DcMat& d = dc[i];
+      const int n = m.n, np = m.np, kb = m.nbt - 1 - tstep, j0 = kb * BT, nbp = std::min(BT, np - j0), K = np - j0;
+      float* ZT = d.Q[d.result_buf ^ 1];
+      float* Y = (float*)(base + m.Y);
+      float* Y2 = (float*)(base + m.Y2);
+      // Y = ZT[:, j0:] V_k[j0:, :]
+      GroupedGemm a = plain(ZT + j0, np, t.VT + (size_t)j0 * t.ldv + j0, t.ldv, Y, BT, n, nbp, K);
+      if (K > 1024 && grouped_gemm_tc_ok(a)) { a.splits = ceil_div(K, 512); a.slab = (float*)(base + m.slabY); a.slab_stride = (int64_t)n * BT; }
+      g1.push_back(a);
+      // Y2 = Y T_k^T
+      g2.push_back(plain(Y, BT, (float*)(base + m.Tm) + (size_t)kb * BT * BT, BT, Y2, BT, n, nbp, nbp));
+      // ZT[:, j0:] -= Y2 V_k[j0:, :]^T
+      GroupedGemm c = plain(Y2, BT, t.Vb + (size_t)kb * np * BT + (size_t)j0 * BT, BT, ZT + j0, np, n, K, nbp);
+      c.alpha = -1.f; c.mode = 1;
+      g3.push_back(c);
+    }
+    if ((rc = launch_grouped_gemm(g1.data(), (int)g1.size(), gws, L.gws_bytes, s))) return rc;
+    if ((rc = launch_grouped_gemm(g2.data(), (int)g2.size(), gws, L.gws_bytes, s))) return rc;
+    if ((rc = launch_grouped_gemm(g3.data(), (int)g3.size(), gws, L.gws_bytes, s))) return rc;
+  }
+  for (int i = 0; i < count; ++i) {
+    const MatLayout& m = L.m[i];
     const DcMat& d = dc[i];
     const int n = m.n, np = m.np;
-    cudaStream_t s = spread ? pool.st[i % StreamPool::N] : s_main;
-    float* Z = d.Q[d.result_buf];
-    float* ZT = d.Q[d.result_buf ^ 1];
-    transpose_ld_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32)), dim3(32, 8), 0, s>>>(Z, np, ZT, np, n, n);
-    KFAC_LAUNCH_CHECK();
-    float* VTt = t.A;          // nbt blocks of (np x BT): V_k T_k   (the UT workspace is dead after stedc)
-    float* Y = Z;              // np x BT scratch (Z is dead after the transpose)
-    for (int kb = 0; kb < m.nbt; ++kb) {
-      const int j0 = kb * BT, nb = std::min(BT, n - j0);
-      GemmArgs g{};            // VTt_k[r][i'] = sum_i VT[j0 + i][r] T_k[i][i']   (fp32 SIMT, strided A)
-      g.A = t.VT + (size_t)j0 * t.ldv + j0; g.sa_m = 1; g.sa_k = t.ldv;
-      g.B = (float*)(base + m.Tm) + (size_t)kb * BT * BT; g.sb_k = BT; g.sb_n = 1;
-      g.C = VTt + (size_t)kb * np * BT + (size_t)j0 * BT; g.ldc = BT;
-      g.M = np - j0; g.N = BT; g.K = nb; g.batch = 1; g.splitk = 1; g.alpha = 1.f; g.beta = 0.f;
-      if ((rc = launch_gemm(g, s))) return rc;
-    }
-    for (int kb = m.nbt - 1; kb >= 0; --kb) {
-      const int j0 = kb * BT, nbp = std::min(BT, np - j0);
-      // Y = ZT[:, j0:] V_k[j0:, :]   (n x nbp)
-      if ((rc = gemm_tn_plain(ZT + j0, np, t.VT + (size_t)j0 * t.ldv + j0, t.ldv, Y, BT, n, nbp, np - j0, s))) return rc;
-      // ZT[:, j0:] -= Y (V_k T_k)[j0:, :]^T
-      if ((rc = gemm_tn_acc(Y, BT, VTt + (size_t)kb * np * BT + (size_t)j0 * BT, BT, ZT + j0, np, n, np - j0, nbp, -1.f, s)))
-        return rc;
-    }
+    const float* ZT = d.Q[d.result_buf ^ 1];
     const int ldq = items[i].ldq > 0 ? items[i].ldq : n;
     if (items[i].QT) {
       copy_rows_kernel<<<std::min(2048, ceil_div((int64_t)n * n, 256)), 256, 0, s>>>(ZT, np, items[i].QT, ldq, n, n);
@@ -338,7 +368,6 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     clamp_copy_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d.d, items[i].d, n);
     KFAC_LAUNCH_CHECK();
   }
-  if (spread && (rc = pool.join(s_main))) return rc;
   return KFAC_OK;
 }
 
@@ -365,7 +394,7 @@ extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e
   t.A = (float*)(base + oA); t.VT = (float*)(base + oVT); t.tau = (float*)(base + oTau); t.d = (float*)(base + oD);
   t.e = (float*)(base + oE); t.Vp = (float*)(base + oVp); t.Wp = (float*)(base + oWp); t.part = (float*)(base + oPart);
   t.col = (float*)(base + oCol); t.cpart = (float*)(base + oC); t.bar = (unsigned int*)(base + oBar);
-  t.n = n; t.np = np; t.nblk = nblk; t.ldv = np;
+  t.n = n; t.np = np; t.nblk = nblk; t.ldv = np; t.Vb = nullptr;
   pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)np * np, 256)), 256, 0, s>>>(F, n, t.A, np);
   KFAC_LAUNCH_CHECK();
   KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)np * np * 4, s));

@@ -7,17 +7,20 @@
 // Replaces torch.linalg.eigh of kfac/layers/eigen.py:310,331 (LAPACK ssyevd = the same three stages).
 #pragma once
 #include "common.cuh"
+#include "gemm_grouped.cuh"
 
 namespace kfac {
 
 constexpr int TRD_NB = 32;        // panel width (columns per block reflector of the reduction)
 constexpr int TRD_T = 64;         // tile edge of the lower-triangle tiling
 constexpr int TRD_THREADS = 1024; // 4 sub-groups of 8 warps
+constexpr int TRD_BT = 128;       // Householder vectors per block reflector of the back-transformation
 constexpr int TRD_CP = 72;        // floats of per-CTA partial scalars: [0,32) W^T v, [32,64) V^T v, 64 v^T A v, 65 |x|^2
 
 struct TrdMat {
   float* A;        // np x np working copy of F (zero padded); only tiles I >= J are kept up to date
   float* VT;       // n x ldv: row j = Householder vector v_j (v_j[j+1] = 1, zero for r <= j)
+  float* Vb;       // optional: the same vectors as row-major blocks, block kb = reflectors [kb*TRD_BT, ..): Vb[kb*np*TRD_BT + r*TRD_BT + i]
   float* tau;      // n
   float* d;        // n     diagonal of T
   float* e;        // n     sub-diagonal of T (e[j] couples j, j+1)
@@ -51,7 +54,7 @@ struct DcMat {
 
 struct DcPlanHost;   // opaque (stedc.cu)
 // workspace bytes for the plan tables (merge lists, leaf descriptors) of a batch
-size_t stedc_plan_bytes(const int* n, int count);
+size_t stedc_plan_bytes(const int* n, int count);   // includes the grouped-GEMM tables
 // eigen-decomposition of `count` tridiagonal matrices; d_mats/h_mats describe them (device pointers inside);
 // plan_ws: device scratch of stedc_plan_bytes(); all work is enqueued on `s`
 int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, cudaStream_t s);

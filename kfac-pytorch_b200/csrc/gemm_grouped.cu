@@ -28,6 +28,7 @@ struct alignas(128) GProb {
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
   int64_t slab_stride;             // != 0: D is the slab base, split sp stores to D + sp * slab_stride
+  int mode;                        // 0 store, 1 read-modify-write accumulate, 2 atomicAdd
   float* peerD[7]; int npeer;
 };
 
@@ -80,7 +81,20 @@ struct GroupedPolicy {
       }
       v[j] = x;
     }
+    if (p.mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nb + j < p.N) atomicAdd(drow + j, v[j]);
+      return;
+    }
     if ((p.ldd & 3) == 0 && nb + 32 <= p.N) {
+      if (p.mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 o = *reinterpret_cast<const float4*>(drow + j);
+          v[j] += o.x; v[j + 1] += o.y; v[j + 2] += o.z; v[j + 3] += o.w;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -95,7 +109,7 @@ struct GroupedPolicy {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (nb + j >= p.N) continue;
-        drow[j] = v[j];
+        drow[j] = (p.mode == 1) ? drow[j] + v[j] : v[j];
         for (int q = 0; q < p.npeer; ++q) p.peerD[q][(int64_t)m * p.ldd + nb + j] = v[j];
       }
     }
@@ -153,16 +167,17 @@ int launch_grouped_gemm(const GroupedGemm* probs, int count, void* ws, size_t ws
     const GroupedGemm& g = probs[i];
     if (g.M <= 0 || g.N <= 0 || g.K <= 0) continue;
     const int splits = std::max(1, g.splits);
-    if (splits > 1 && (!g.slab || g.epi != EPI_NONE || g.npeer > 0)) {
-      set_error("grouped gemm: split-K needs a slab and the plain epilogue");
+    if (splits > 1 && ((!g.slab && g.mode != 2) || g.epi != EPI_NONE || g.npeer > 0 || g.mode == 1)) {
+      set_error("grouped gemm: split-K needs a slab (or atomic mode) and the plain epilogue");
       return KFAC_ERR_BAD_ARG;
     }
+    if (g.mode != 0 && (g.epi != EPI_NONE || g.npeer > 0)) { set_error("grouped gemm: accumulate modes need the plain epilogue"); return KFAC_ERR_BAD_ARG; }
     if (!grouped_gemm_tc_ok(g)) {
       // small / unaligned problems: one SIMT launch each (fp32, no split needed)
       GemmArgs a{};
       a.A = g.A; a.sa_m = g.lda; a.sa_k = 1; a.B = g.B; a.sb_k = 1; a.sb_n = g.ldb;
       a.C = g.D; a.ldc = g.ldd; a.M = g.M; a.N = g.N; a.K = g.K; a.batch = 1; a.splitk = 1;
-      a.alpha = g.alpha; a.beta = 0.f; a.epi = g.epi; a.E = g.E; a.lde = g.lde; a.dg = g.dg; a.da = g.da; a.damping = g.damping;
+      a.alpha = g.alpha; a.beta = g.mode == 0 ? 0.f : 1.f; a.epi = g.epi; a.E = g.E; a.lde = g.lde; a.dg = g.dg; a.da = g.da; a.damping = g.damping;
       int rc = launch_gemm(a, s);
       if (rc) return rc;
       if (g.npeer > 0) {
@@ -185,7 +200,10 @@ int launch_grouped_gemm(const GroupedGemm* probs, int count, void* ws, size_t ws
     p.kb_total = ceil_div(g.K, GBK);
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.splits = ceil_div(p.kb_total, p.kb_per_split);
-    if (p.splits > 1) {
+    p.mode = g.mode;
+    if (p.splits > 1 && g.mode == 2) {
+      p.D = g.D; p.slab_stride = 0;
+    } else if (p.splits > 1) {
       p.D = g.slab; p.slab_stride = g.slab_stride;
       red.push_back(RProb{g.slab, g.D, g.slab_stride, p.splits, g.N, (int)g.ldd, red_total});
       red_total += (long long)g.M * g.ldd;

@@ -12,8 +12,9 @@ struct GroupedGemm {
   float alpha;
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;   // GemmEpilogue
   float* peerD[7]; int npeer;      // fused broadcast: tiles are also stored into these peer copies of D
-  int splits;                      // > 1: deterministic split-K through `slab` (plain epilogue, no peers)
+  int splits;                      // > 1: split-K -- deterministic through `slab` (plain epilogue, no peers), or mode 2
   float* slab; int64_t slab_stride;
+  int mode;                        // 0: D = ..., 1: D += ... (read-modify-write, splits == 1), 2: atomicAdd into D (caller zeroes D)
 };
 
 size_t grouped_gemm_ws_bytes(int count);

@@ -454,8 +454,10 @@ size_t stedc_plan_bytes(const int* n, int count) {
   make_plan(n, count, pl);
   size_t merges = 0;
   for (auto& l : pl.levels) merges += l.size();
+  size_t widest = 1;
+  for (auto& l : pl.levels) widest = std::max(widest, l.size());
   return align_up(sizeof(DcCut) * pl.cuts.size() + 256, 256) + align_up(sizeof(DcLeaf) * pl.leaves.size() + 256, 256) +
-         align_up(sizeof(DcMerge) * merges + 256 * (pl.levels.size() + 1), 256);
+         align_up(sizeof(DcMerge) * merges + 256 * (pl.levels.size() + 1), 256) + align_up(grouped_gemm_ws_bytes((int)widest), 256);
 }
 
 int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, cudaStream_t s) {
@@ -470,6 +472,10 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
   DcLeaf* d_leaves = (DcLeaf*)take(sizeof(DcLeaf) * std::max<size_t>(1, pl.leaves.size()));
   std::vector<DcMerge*> d_levels;
   for (auto& l : pl.levels) d_levels.push_back((DcMerge*)take(sizeof(DcMerge) * l.size()));
+  size_t widest = 1;
+  for (auto& l : pl.levels) widest = std::max(widest, l.size());
+  const size_t gws_bytes = grouped_gemm_ws_bytes((int)widest);
+  void* gws = take(gws_bytes);
   if (off > plan_bytes) { set_error("stedc: plan workspace too small (%zu < %zu)", plan_bytes, off); return KFAC_ERR_WORKSPACE; }
   if (!pl.cuts.empty())
     KFAC_CUDA(cudaMemcpyAsync(d_cuts, pl.cuts.data(), sizeof(DcCut) * pl.cuts.size(), cudaMemcpyHostToDevice, s));
@@ -515,20 +521,23 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
     KFAC_LAUNCH_CHECK();
     dc_copy_d_kernel<<<dim3(ceil_div(mmax, 256), nm), 256, 0, s>>>(d_mats, d_levels[l]);
     KFAC_LAUNCH_CHECK();
-    // one GEMM per merge, independent of each other: spread over the side streams
-    StreamPool& pool = stream_pool();
-    const bool spread = nm > 1;
-    if (spread) { const int rc = pool.fork(s); if (rc) return rc; }
-    int gi = 0;
+    // Q_new = Q_old U~ for every merge of the level: ONE grouped tcgen05 launch.  Long reductions are split into
+    // chains of <= 512 (the tensor-core accumulator truncates) and added atomically into the zeroed target block.
+    std::vector<GroupedGemm> gg;
     for (auto& mg : lv) {
       const DcMat& mt = h_mats[mg.mat];
       const int m = mg.hi - mg.lo;
       const int64_t o = (int64_t)mg.lo * mt.ld + mg.lo;
-      cudaStream_t gs = spread ? pool.st[gi++ % StreamPool::N] : s;
-      const int rc = gemm_tn_plain(mt.Q[mg.src] + o, mt.ld, mt.UT + o, mt.ld, mt.Q[mg.src ^ 1] + o, mt.ld, m, m, m, gs);
-      if (rc) return rc;
+      GroupedGemm g{};
+      g.A = mt.Q[mg.src] + o; g.lda = mt.ld; g.B = mt.UT + o; g.ldb = mt.ld; g.D = mt.Q[mg.src ^ 1] + o; g.ldd = mt.ld;
+      g.M = m; g.N = m; g.K = m; g.alpha = 1.f; g.epi = EPI_NONE; g.splits = 1;
+      if (m > 1024 && grouped_gemm_tc_ok(g)) {
+        g.splits = ceil_div(m, 512); g.mode = 2;
+        KFAC_CUDA(cudaMemset2DAsync(g.D, (size_t)mt.ld * 4, 0, (size_t)m * 4, (size_t)m, s));
+      }
+      gg.push_back(g);
     }
-    if (spread) { const int rc = pool.join(s); if (rc) return rc; }
+    { const int rc = launch_grouped_gemm(gg.data(), (int)gg.size(), gws, gws_bytes, s); if (rc) return rc; }
   }
   for (int i = 0; i < count; ++i) h_mats[i].result_buf = pl.result_buf[i];
   return KFAC_OK;

@@ -179,7 +179,12 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       const int per = (n + ncta - 1) / ncta;
       const int a = cta * per, b = min(n, a + per);
       float* vt = mt.VT + (int64_t)s * mt.ldv;
-      for (int r = a + tid; r < b; r += blockDim.x) vt[r] = vfix(r, raw_v(r));
+      float* vb = mt.Vb ? mt.Vb + (int64_t)(s / TRD_BT) * np * TRD_BT + (s % TRD_BT) : nullptr;
+      for (int r = a + tid; r < b; r += blockDim.x) {
+        const float v = vfix(r, raw_v(r));
+        vt[r] = v;
+        if (vb) vb[(int64_t)r * TRD_BT] = v;
+      }
     }
     // symmetric product with the lower tiles of this sub-group
     float vav = 0.f;
@@ -228,21 +233,25 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         }
       }
     }
-    // per-CTA partials of p1 = W^T v, p2 = V^T v over the owned row blocks (lane = panel column)
+    // per-CTA partials of p1 = W^T v, p2 = V^T v: the rows of the CTA's row blocks are spread over its 32 warps
+    // (warp w takes row 32 k + w, lane = panel column); all loads of up to 4 blocks are issued before they are used
     float p1 = 0.f, p2 = 0.f;
     if (P > 0) {
-      for (int k = cta + ncta * warp; k < nrb; k += ncta * 32) {
-        if (k < rb_first) continue;
-        const int rbase = k * 32;
-        const float vl = vfix(rbase + lane, raw_v(rbase + lane));      // lane j holds v[rbase + j]
-        const int rend = min(32, n - rbase);
-#pragma unroll 4
-        for (int j = 0; j < rend; ++j) {
-          const float v = __shfl_sync(0xffffffffu, vl, j);
-          if (lane < P) {
-            p1 = fmaf(__ldcg(&mt.Wp[(int64_t)(rbase + j) * NB + lane]), v, p1);
-            p2 = fmaf(__ldcg(&mt.Vp[(int64_t)(rbase + j) * NB + lane]), v, p2);
-          }
+      for (int k0 = cta; k0 < nrb; k0 += 4 * ncta) {
+        float wv[4], vv[4], rw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = k0 + q * ncta, r = k * 32 + warp;
+          const bool ok = k < nrb && k >= rb_first && r < n && lane < P;
+          rw[q] = (k < nrb && k >= rb_first) ? raw_v(r) : 0.f;
+          wv[q] = ok ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
+          vv[q] = ok ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float v = vfix((k0 + q * ncta) * 32 + warp, rw[q]);
+          p1 = fmaf(wv[q], v, p1);
+          p2 = fmaf(vv[q], v, p2);
         }
       }
     }
@@ -301,45 +310,60 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       }
       __syncthreads();
       const float ytv = sc[68], w1 = sc[69];
-      // own row blocks, lane = row: y = A v - V p1 - W p2, w, next effective column x'
+      // own row blocks (passes of up to BP blocks): (1) every warp gathers a slice of the tile partials of all rows
+      // of the block (lane = row, warp = tile index mod 32) into shared memory, (2) warp w finishes row 32 k + w
+      // (lane = panel column): y, w, the next effective column x' and its norm partial
+      constexpr int BP = 4;
+      float* Gs = stage;                               // [BP][32 warps][33]
       float sig = 0.f;
-      for (int k = cta + ncta * warp; k < nrb; k += ncta * 32) {
-        if (k < rb_first) continue;
-        const int r = k * 32 + lane;
-        const bool act = r >= s + 1 && r < n;
-        float y = 0.f;
-        if (act)
-          for (int X = b0; X < nblk; ++X) y += __ldcg(&mt.part[(int64_t)X * np + r]);
-        const float v = act ? vfix(r, raw_v(r)) : 0.f;
-        const float acol = (act && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
-        float corr = 0.f, xs = 0.f;
-        if (act) {
-          const float4* vp = reinterpret_cast<const float4*>(&mt.Vp[(int64_t)r * NB]);
-          const float4* wp = reinterpret_cast<const float4*>(&mt.Wp[(int64_t)r * NB]);
-          for (int i4 = 0; i4 * 4 < P; ++i4) {
-            const float4 vv = __ldcg(vp + i4), ww = __ldcg(wp + i4);
-            const float4 q1 = *reinterpret_cast<const float4*>(&sc[i4 * 4]), q2 = *reinterpret_cast<const float4*>(&sc[32 + i4 * 4]);
-            const float4 vr4 = *reinterpret_cast<const float4*>(&s_vrow[i4 * 4]), wr4 = *reinterpret_cast<const float4*>(&s_wrow[i4 * 4]);
-            // entries i >= P of the panel row are stale: mask them (sc / s_vrow / s_wrow are zero there except column P)
-            const float m0 = (i4 * 4 + 0 < P) ? 1.f : 0.f, m1 = (i4 * 4 + 1 < P) ? 1.f : 0.f, m2 = (i4 * 4 + 2 < P) ? 1.f : 0.f,
-                        m3 = (i4 * 4 + 3 < P) ? 1.f : 0.f;
-            corr += m0 * (vv.x * q1.x + ww.x * q2.x) + m1 * (vv.y * q1.y + ww.y * q2.y) + m2 * (vv.z * q1.z + ww.z * q2.z) +
-                    m3 * (vv.w * q1.w + ww.w * q2.w);
-            xs += m0 * (vv.x * wr4.x + ww.x * vr4.x) + m1 * (vv.y * wr4.y + ww.y * vr4.y) + m2 * (vv.z * wr4.z + ww.z * vr4.z) +
-                  m3 * (vv.w * wr4.w + ww.w * vr4.w);
+      for (int k0 = cta; k0 < nrb; k0 += BP * ncta) {
+        if (k0 + (BP - 1) * ncta < rb_first) continue;   // nothing active in this pass (uniform)
+        // ---- loads (all independent)
+        float g[BP][3];
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = k0 + q * ncta, r = k * 32 + lane;
+          const bool okb = k < nrb && k >= rb_first && r < n;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int X = b0 + warp + 32 * j;
+            g[q][j] = (okb && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f;
           }
         }
-        if (act) {
-          y -= corr;
-          const float w = tau * (y - 0.5f * tau * ytv * v);
-          mt.Wp[(int64_t)r * NB + P] = w;
-          mt.Vp[(int64_t)r * NB + P] = v;
-          if (r >= s + 2) {
-            const float x = acol - xs - (v * w1 + w);            // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
-            col[r] = x;
-            if (r >= s + 3) sig = fmaf(x, x, sig);
+        float vr[BP], wr[BP], ac[BP], rw[BP];
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = k0 + q * ncta, r = k * 32 + warp;
+          const bool okr = k < nrb && k >= rb_first && r >= s + 1 && r < n;
+          vr[q] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
+          wr[q] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
+          ac[q] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
+          rw[q] = okr ? raw_v(r) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < BP; ++q) Gs[(q * 32 + warp) * 33 + lane] = (g[q][0] + g[q][1]) + g[q][2];
+        __syncthreads();
+        const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
+        const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = k0 + q * ncta, r = k * 32 + warp;
+          if (!(k < nrb && k >= rb_first && r >= s + 1 && r < n)) continue;        // warp-uniform
+          const float v = vfix(r, rw[q]);
+          const float y = warp_sum(Gs[(q * 32 + lane) * 33 + warp] - (vr[q] * p1l + wr[q] * p2l));
+          const float xs = warp_sum(vr[q] * wsl + wr[q] * vsl);
+          if (lane == 0) {
+            const float w = tau * (y - 0.5f * tau * ytv * v);
+            mt.Wp[(int64_t)r * NB + P] = w;
+            mt.Vp[(int64_t)r * NB + P] = v;
+            if (r >= s + 2) {
+              const float x = ac[q] - xs - (v * w1 + w);          // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
+              col[r] = x;
+              if (r >= s + 3) sig = fmaf(x, x, sig);
+            }
           }
         }
+        if (k0 + BP * ncta < nrb) __syncthreads();       // the next pass overwrites Gs
       }
       sig = warp_sum(sig);
       if (lane == 0) red[warp] = sig;

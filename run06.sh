@@ -1,0 +1,4 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sytrd_kernel -s 1 -c 1 -o gpurun_out/r2_06_sytrd4608 python tests/sytrd_probe.py 4608 148 > gpurun_out/r2_06_ncu1.log 2>&1
+tail -n 3 gpurun_out/r2_06_ncu1.log
