@@ -129,8 +129,10 @@ void make_layout(const int* n, int count, Layout& L) {
 // ---- CTA-group schedule of the tridiagonalisation kernel --------------------------------------
 // model of one matrix on C CTAs: n columns, each t0 (barriers + vector phases) + beta n^2 / C (tile products,
 // averaged over the shrinking trailing matrix)
-constexpr double T0 = 2.6e-6, BETA = 1.1e-11;
-double job_time(int n, int C) { return (double)n * (T0 + BETA * (double)n * n / C); }
+// measured on B200 (tests/test_gpu_direct_eigh.py, profiles/): ~10 us of barrier / dependent-load latency per column
+// + 1 ns per row + the tile products
+constexpr double T0 = 9.9e-6, T1 = 1.0e-9, BETA = 1.2e-11;
+double job_time(int n, int C) { return (double)n * (T0 + T1 * n + BETA * (double)n * n / C); }
 
 void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
   // smallest makespan M such that the CTA-time of all jobs (each sized to finish within M) fits into G * M
@@ -148,7 +150,7 @@ void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
     const double M = 0.5 * (lo + hi);
     double area = 0;
     for (int i = 0; i < count; ++i) { const int C = ctas_for(n[i], M); area += C * job_time(n[i], C); }
-    if (area <= 0.85 * G * M) hi = M; else lo = M;
+    if (area <= 0.9 * G * M) hi = M; else lo = M;
   }
   std::vector<int> order(count), C(count);
   for (int i = 0; i < count; ++i) { order[i] = i; C[i] = ctas_for(n[i], hi); }

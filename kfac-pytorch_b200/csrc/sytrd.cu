@@ -46,8 +46,11 @@ __device__ __forceinline__ void group_barrier(unsigned* bar, unsigned& epoch, in
   }
 }
 
-__device__ __forceinline__ void sub_sync(int sg) {
-  asm volatile("bar.sync %0, %1;" ::"r"(sg + 1), "r"(256) : "memory");
+__device__ __forceinline__ void sub_sync(int sg) {          // 4 sub-groups of 256 threads (tile update)
+  asm volatile("bar.sync %0, %1;" ::"r"(sg + 9), "r"(256) : "memory");
+}
+__device__ __forceinline__ void sub_sync8(int sg8) {        // 8 sub-groups of 128 threads (symmetric product)
+  asm volatile("bar.sync %0, %1;" ::"r"(sg8 + 1), "r"(128) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -60,6 +63,32 @@ constexpr int MAXT = 256;                   // owned tiles per sub-group (list i
 constexpr int NCP = 5;                      // ceil(max CTAs per group / 32)
 
 __device__ __forceinline__ float sum5(const float (&x)[NCP]) { return ((x[0] + x[1]) + (x[2] + x[3])) + x[4]; }
+
+// sums of 16 per-lane values over the warp with 16 shuffles: afterwards every lane holds the complete sum of value
+// number (lane >> 1) & 15
+__device__ __forceinline__ float reduce16(float (&r)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = (lane & 16) ? r[i + 8] : r[i], send = (lane & 16) ? r[i] : r[i + 8];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = (lane & 8) ? r[i + 4] : r[i], send = (lane & 8) ? r[i] : r[i + 4];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = (lane & 4) ? r[i + 2] : r[i], send = (lane & 4) ? r[i] : r[i + 2];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float keep = (lane & 2) ? r[1] : r[0], send = (lane & 2) ? r[0] : r[1];
+    r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+  return r[0];
+}
 
 // sums of 8 per-lane values over the warp with 9 shuffles: afterwards every lane holds the complete sum
 // of value number rowid(lane) = bit2 | bit3 << 1 | bit4 << 2 of its lane index
@@ -89,14 +118,17 @@ __device__ __forceinline__ float reduce8(float (&r)[8], int lane) {
 __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem) {
   const int n = mt.n, np = mt.np, nblk = mt.nblk;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sg = warp >> 3, sw = warp & 7;           // sub-group (tile worker) and warp within it
-  const int G = ncta * 4, sgid = cta * 4 + sg;       // tile owners
+  const int sg = warp >> 3;                          // update sub-group (256 threads)
+  const int G = ncta * 4, sgid = cta * 4 + sg;       // tile owners of the rank-2NB update
+  const int sg8 = warp >> 2, sw4 = warp & 3;         // product sub-group (128 threads) and warp within it
+  const int G8 = ncta * 8, sgid8 = cta * 8 + sg8;    // tile owners of the symmetric product
   const int GW = ncta * 32, gw = cta * 32 + warp;    // row owners: rows r = gw (mod GW)
   float* stage = smem;                               // 4 * SUB_STAGE (update staging / column partial sums)
   float* red = stage + 4 * SUB_STAGE;                // 32 x 66
   float* sc = red + 32 * 66;                         // 160 scalars: [0,32) p1, [32,64) p2, 64 vAv, 66.. misc, [96,128) vrow, [128,160) wrow
   short2* tlist = reinterpret_cast<short2*>(sc + 160) + sg * MAXT;
-  __shared__ int s_ntile[4];
+  short2* tlist8 = reinterpret_cast<short2*>(sc + 160) + 4 * MAXT + sg8 * MAXT;
+  __shared__ int s_ntile[12];
   unsigned epoch = 0;
   float* const col = mt.col;
   float* const cpart = mt.cpart;
@@ -116,9 +148,18 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     }
     s_ntile[sg] = cnt;
   }
+  if ((tid & 127) == 0) {
+    int cnt = 0;
+    for (int I = 0; I < nblk; ++I) {
+      const int tri = (int)(((int64_t)I * (I + 1) / 2) % G8);
+      for (int J = ((sgid8 - tri) % G8 + G8) % G8; J <= I; J += G8)
+        if (cnt < MAXT) tlist8[cnt++] = make_short2((short)I, (short)J);
+    }
+    s_ntile[4 + sg8] = cnt;
+  }
   __syncthreads();
-  const int ntile = s_ntile[sg];
-  int tfirst = 0;                                    // tiles before this index are dead (I < b0)
+  const int ntile = s_ntile[sg], ntile8 = s_ntile[4 + sg8];
+  int tfirst = 0, tfirst8 = 0;                       // tiles before these indices are dead (I < b0)
 
   // ---- column 0: x = A[1:, 0], |x[1:]|^2 partials, d[0]
   {
@@ -150,6 +191,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     const int b0 = (s + 1) / T;
     const int rb_first = (s + 1) / 32;               // first row block with an active row
     while (tfirst < ntile && tlist[tfirst].x < b0) ++tfirst;
+    while (tfirst8 < ntile8 && tlist8[tfirst8].x < b0) ++tfirst8;
     // =========================================================== phase C: Householder scalars (warp 0)
     if (warp == 0) {
       float sgp[NCP];
@@ -186,48 +228,46 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         if (vb) vb[(int64_t)r * TRD_BT] = v;
       }
     }
-    // symmetric product with the lower tiles of this sub-group
+    // symmetric product with the lower tiles of this sub-group (128 threads: a warp takes 16 rows of the tile)
     float vav = 0.f;
     {
-      float* cs = stage + sg * (8 * T);              // column partial sums: [8 warps][64]
-      const int st_tid = tid & 255;
-      for (int ti = tfirst; ti < ntile; ++ti) {
-        const int I = tlist[ti].x, J = tlist[ti].y;
+      float* cs = stage + sg8 * (4 * T);             // column partial sums: [4 warps][64]
+      const int st_tid = tid & 127;
+      for (int ti = tfirst8; ti < ntile8; ++ti) {
+        const int I = tlist8[ti].x, J = tlist8[ti].y;
         if (J < b0) continue;
-        const int rb = I * T + sw * 8, c0 = J * T + 2 * lane;
-        float2 a[8];
+        const int rb = I * T + sw4 * 16, c0 = J * T + 2 * lane;
+        float2 a[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(&A[(int64_t)(rb + k) * np + c0]));
+        for (int k = 0; k < 16; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(&A[(int64_t)(rb + k) * np + c0]));
         const float rj0 = raw_v(c0), rj1 = raw_v(c0 + 1);
-        const float ri = raw_v(rb + (lane & 7));
+        const float ri = raw_v(rb + (lane & 15));
         const float vj0 = vfix(c0, rj0), vj1 = vfix(c0 + 1, rj1);
-        const float vi_l = vfix(rb + (lane & 7), ri);
-        float rs[8];
+        const float vi_l = vfix(rb + (lane & 15), ri);
+        float rs[16];
         float c0acc = 0.f, c1acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 16; ++k) {
           const float vi = __shfl_sync(0xffffffffu, vi_l, k);
           rs[k] = fmaf(a[k].x, vj0, a[k].y * vj1);
           c0acc = fmaf(a[k].x, vi, c0acc);
           c1acc = fmaf(a[k].y, vi, c1acc);
         }
-        const float tot = reduce8(rs, lane);
-        const int rid = ((lane >> 2) & 1) | (((lane >> 3) & 1) << 1) | (((lane >> 4) & 1) << 2);
+        const float tot = reduce16(rs, lane);
+        const int rid = (lane >> 1) & 15;
         const float vi_r = __shfl_sync(0xffffffffu, vi_l, rid);
-        if ((lane & 3) == 0) {
+        if ((lane & 1) == 0) {
           mt.part[(int64_t)J * np + rb + rid] = tot;
           const float t = tot * vi_r;
           vav += (I == J) ? t : 2.f * t;
         }
         if (I != J) {
-          sub_sync(sg);                              // previous tile's readers are done with cs
-          cs[sw * T + 2 * lane] = c0acc;
-          cs[sw * T + 2 * lane + 1] = c1acc;
-          sub_sync(sg);
+          sub_sync8(sg8);                            // previous tile's readers are done with cs
+          cs[sw4 * T + 2 * lane] = c0acc;
+          cs[sw4 * T + 2 * lane + 1] = c1acc;
+          sub_sync8(sg8);
           if (st_tid < T) {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) t += cs[w * T + st_tid];
+            const float t = (cs[st_tid] + cs[T + st_tid]) + (cs[2 * T + st_tid] + cs[3 * T + st_tid]);
             mt.part[(int64_t)I * np + J * T + st_tid] = t;
           }
         }
@@ -269,7 +309,36 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     group_barrier(mt.bar, epoch, ncta);
     // =========================================================== phase B
     {
-      // cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
+      // ---- every global load of the phase is issued first (they are mutually independent):
+      // (1) the tile partials / panel rows / column entries of the first pass over this CTA's row blocks
+      constexpr int BP = 4;
+      float* Gs = stage;                               // [BP][32 warps][33]
+      float g[BP][3], vr[BP], wr[BP], ac[BP], rw[BP];
+      auto load_pass = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = k0 + q * ncta, r = k * 32 + lane;
+          const bool okb = k < nrb && k >= rb_first && r < n;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int X = b0 + warp + 32 * j;
+            g[q][j] = (okb && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = k0 + q * ncta, r = k * 32 + warp;
+          const bool okr = k < nrb && k >= rb_first && r >= s + 1 && r < n;
+          vr[q] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
+          wr[q] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
+          ac[q] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
+          rw[q] = okr ? raw_v(r) : 0.f;
+        }
+      };
+      int k0 = cta;
+      while (k0 < nrb && k0 + (BP - 1) * ncta < rb_first) k0 += BP * ncta;     // first pass with an active block
+      load_pass(k0);
+      // (2) cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
       {
         float ca[NCP], cb[NCP], cc[NCP];
         const bool need = warp < P;
@@ -281,70 +350,43 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
           cb[j] = (in && need) ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
           cc[j] = (in && warp == 0) ? __ldcg(&cpart[64 * ncta + c]) : 0.f;
         }
+        // (3) row s+1 (warp 1): raw loads now, the rest after the sums are published
+        const int r1 = s + 1;
+        float y1p[3] = {0.f, 0.f, 0.f}, vrow = 0.f, wrow = 0.f, a11 = 0.f;
+        if (warp == 1) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; y1p[j] = X < nblk ? __ldcg(&mt.part[(int64_t)X * np + r1]) : 0.f; }
+          vrow = (lane < P) ? __ldcg(&mt.Vp[(int64_t)r1 * NB + lane]) : 0.f;
+          wrow = (lane < P) ? __ldcg(&mt.Wp[(int64_t)r1 * NB + lane]) : 0.f;
+          a11 = __ldcg(&A[(int64_t)r1 * np + r1]);
+        }
         if (need || warp == 0) {
           const float sa = warp_sum(sum5(ca)), sb = warp_sum(sum5(cb));
           if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; }
           if (warp == 0) { const float scv = warp_sum(sum5(cc)); if (lane == 0) sc[64] = scv; }
         } else if (lane == 0) { sc[warp] = 0.f; sc[32 + warp] = 0.f; }
+        __syncthreads();
+        if (warp == 1) {
+          const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
+          const float ytv1 = sc[64] - 2.f * warp_sum(p1l * p2l);
+          const float y1 = warp_sum((y1p[0] + y1p[1]) + y1p[2] - (vrow * p1l + wrow * p2l));
+          const float w1v = tau * (y1 - 0.5f * tau * ytv1);          // v[s+1] = 1
+          if (lane == P) { vrow = 1.f; wrow = w1v; }
+          s_vrow[lane] = vrow; s_wrow[lane] = wrow;
+          const float dd = warp_sum(vrow * wrow);
+          if (lane == 0) { sc[68] = ytv1; sc[69] = w1v; if (cta == 0) mt.d[r1] = a11 - 2.f * dd; }
+        }
       }
-      // row s+1 (warp 1): raw loads now, the rest after the sums are published
-      const int r1 = s + 1;
-      float y1p[3] = {0.f, 0.f, 0.f}, vrow = 0.f, wrow = 0.f, a11 = 0.f;
-      if (warp == 1) {
+      // the gathered partial sums go through shared memory: warp = tile index class, lane = row  ->  lane = class, warp = row
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; y1p[j] = X < nblk ? __ldcg(&mt.part[(int64_t)X * np + r1]) : 0.f; }
-        vrow = (lane < P) ? __ldcg(&mt.Vp[(int64_t)r1 * NB + lane]) : 0.f;
-        wrow = (lane < P) ? __ldcg(&mt.Wp[(int64_t)r1 * NB + lane]) : 0.f;
-        a11 = __ldcg(&A[(int64_t)r1 * np + r1]);
-      }
-      __syncthreads();
-      if (warp == 1) {
-        const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
-        const float ytv = sc[64] - 2.f * warp_sum(p1l * p2l);
-        const float y1 = warp_sum((y1p[0] + y1p[1]) + y1p[2] - (vrow * p1l + wrow * p2l));
-        const float w1 = tau * (y1 - 0.5f * tau * ytv);            // v[s+1] = 1
-        if (lane == P) { vrow = 1.f; wrow = w1; }
-        s_vrow[lane] = vrow; s_wrow[lane] = wrow;
-        const float dd = warp_sum(vrow * wrow);
-        if (lane == 0) { sc[68] = ytv; sc[69] = w1; if (cta == 0) mt.d[r1] = a11 - 2.f * dd; }
-      }
+      for (int q = 0; q < BP; ++q) Gs[(q * 32 + warp) * 33 + lane] = (g[q][0] + g[q][1]) + g[q][2];
       __syncthreads();
       const float ytv = sc[68], w1 = sc[69];
-      // own row blocks (passes of up to BP blocks): (1) every warp gathers a slice of the tile partials of all rows
-      // of the block (lane = row, warp = tile index mod 32) into shared memory, (2) warp w finishes row 32 k + w
-      // (lane = panel column): y, w, the next effective column x' and its norm partial
-      constexpr int BP = 4;
-      float* Gs = stage;                               // [BP][32 warps][33]
+      const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
+      const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
       float sig = 0.f;
-      for (int k0 = cta; k0 < nrb; k0 += BP * ncta) {
-        if (k0 + (BP - 1) * ncta < rb_first) continue;   // nothing active in this pass (uniform)
-        // ---- loads (all independent)
-        float g[BP][3];
-#pragma unroll
-        for (int q = 0; q < BP; ++q) {
-          const int k = k0 + q * ncta, r = k * 32 + lane;
-          const bool okb = k < nrb && k >= rb_first && r < n;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int X = b0 + warp + 32 * j;
-            g[q][j] = (okb && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f;
-          }
-        }
-        float vr[BP], wr[BP], ac[BP], rw[BP];
-#pragma unroll
-        for (int q = 0; q < BP; ++q) {
-          const int k = k0 + q * ncta, r = k * 32 + warp;
-          const bool okr = k < nrb && k >= rb_first && r >= s + 1 && r < n;
-          vr[q] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
-          wr[q] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
-          ac[q] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
-          rw[q] = okr ? raw_v(r) : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < BP; ++q) Gs[(q * 32 + warp) * 33 + lane] = (g[q][0] + g[q][1]) + g[q][2];
-        __syncthreads();
-        const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
-        const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
+      for (; k0 < nrb; k0 += BP * ncta) {
+        // warp w finishes row 32 k + w of each block of the pass (lane = panel column): y, w, x' and its norm partial
 #pragma unroll
         for (int q = 0; q < BP; ++q) {
           const int k = k0 + q * ncta, r = k * 32 + warp;
@@ -363,7 +405,13 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
             }
           }
         }
-        if (k0 + BP * ncta < nrb) __syncthreads();       // the next pass overwrites Gs
+        if (k0 + BP * ncta < nrb) {                      // another pass (small groups only): reload, regather
+          __syncthreads();
+          load_pass(k0 + BP * ncta);
+#pragma unroll
+          for (int q = 0; q < BP; ++q) Gs[(q * 32 + warp) * 33 + lane] = (g[q][0] + g[q][1]) + g[q][2];
+          __syncthreads();
+        }
       }
       sig = warp_sum(sig);
       if (lane == 0) red[warp] = sig;
@@ -446,7 +494,7 @@ __global__ void __launch_bounds__(TRD_THREADS, 1) sytrd_kernel(const TrdMat* mat
 }
 
 size_t trd_smem_bytes(int) {
-  return sizeof(float) * ((size_t)4 * SUB_STAGE + 32 * 66 + 160) + sizeof(short2) * 4 * MAXT + 64;
+  return sizeof(float) * ((size_t)4 * SUB_STAGE + 32 * 66 + 160) + sizeof(short2) * 12 * MAXT + 64;
 }
 
 }  // namespace
