@@ -181,23 +181,27 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   group_barrier(mt.bar, epoch, ncta);
 
   int P = 0;                                         // columns in the current panel
-  // Vector work is organised in ROW BLOCKS of 32 consecutive rows: block k belongs to CTA (k mod ncta), warp
-  // ((k / ncta) mod 32).  A warp works on a block either with lane = panel column (dots) or lane = row (everything
-  // else), so the per-row instruction count is ~5-10 instead of one warp reduction per row and per quantity.
+  // Vector work is organised in ROW BLOCKS of 32 consecutive rows; block k belongs to CTA (k mod ncta) and its rows
+  // are spread over the CTA's 32 warps (warp w takes row 32 k + w).  Code paths without work are skipped by
+  // WARP-UNIFORM branches (the kernel is instruction-issue bound, not bandwidth bound).
   const int nrb = (n + 31) / 32;
   float* s_vrow = sc + 96;                           // 32: V[s+1][:]
   float* s_wrow = sc + 128;                          // 32: W[s+1][:]
+  const int vt_per = (n + ncta - 1) / ncta, vt_a = cta * vt_per, vt_b = min(n, vt_a + vt_per);
+  constexpr int BP = 4;                              // row blocks per pass
+  int kfirst = cta;                                  // first owned row block that still has an active row
   for (int s = 0; s <= n - 2; ++s) {
-    const int b0 = (s + 1) / T;
-    const int rb_first = (s + 1) / 32;               // first row block with an active row
+    const int s1 = s + 1;
+    const int b0 = s1 / T, rb_first = s1 / 32;
     while (tfirst < ntile && tlist[tfirst].x < b0) ++tfirst;
     while (tfirst8 < ntile8 && tlist8[tfirst8].x < b0) ++tfirst8;
+    while (kfirst < rb_first) kfirst += ncta;
     // =========================================================== phase C: Householder scalars (warp 0)
     if (warp == 0) {
       float sgp[NCP];
 #pragma unroll
       for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; sgp[j] = c < ncta ? __ldcg(&cpart[65 * ncta + c]) : 0.f; }
-      const float alpha = __ldcg(&col[s + 1]);
+      const float alpha = __ldcg(&col[s1]);
       const float sigma = warp_sum(sum5(sgp));
       if (lane == 0) {
         float beta, tau, scal;
@@ -213,17 +217,17 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     }
     __syncthreads();
     const float tau = sc[66], scal = sc[67];
-    auto raw_v = [&](int r) { return (r > s + 1 && r < n) ? __ldcg(&col[r]) : 0.f; };
-    auto vfix = [&](int r, float raw) { return r == s + 1 ? 1.f : raw * scal; };
+    // v[r] = 0 (r <= s), 1 (r = s + 1), x[r] * scal (r > s + 1): x is read straight from `col`
+#define TRD_RAW(r) (((r) > s1 && (r) < n) ? __ldcg(col + (r)) : 0.f)
+#define TRD_VFIX(r, raw) ((r) == s1 ? 1.f : (raw) * scal)
     // =========================================================== phase A
     // the Householder vector is kept for the back-transformation (each CTA writes a slice of the row)
-    {
-      const int per = (n + ncta - 1) / ncta;
-      const int a = cta * per, b = min(n, a + per);
+    if (vt_a + tid < vt_b) {
       float* vt = mt.VT + (int64_t)s * mt.ldv;
       float* vb = mt.Vb ? mt.Vb + (int64_t)(s / TRD_BT) * np * TRD_BT + (s % TRD_BT) : nullptr;
-      for (int r = a + tid; r < b; r += blockDim.x) {
-        const float v = vfix(r, raw_v(r));
+      for (int r = vt_a + tid; r < vt_b; r += TRD_THREADS) {
+        const float raw = TRD_RAW(r);
+        const float v = TRD_VFIX(r, raw);
         vt[r] = v;
         if (vb) vb[(int64_t)r * TRD_BT] = v;
       }
@@ -237,13 +241,15 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         const int I = tlist8[ti].x, J = tlist8[ti].y;
         if (J < b0) continue;
         const int rb = I * T + sw4 * 16, c0 = J * T + 2 * lane;
+        const float* ap = A + (int64_t)rb * np + c0;
         float2 a[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(&A[(int64_t)(rb + k) * np + c0]));
-        const float rj0 = raw_v(c0), rj1 = raw_v(c0 + 1);
-        const float ri = raw_v(rb + (lane & 15));
-        const float vj0 = vfix(c0, rj0), vj1 = vfix(c0 + 1, rj1);
-        const float vi_l = vfix(rb + (lane & 15), ri);
+        for (int k = 0; k < 16; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(ap + (int64_t)k * np));
+        const float rj0 = TRD_RAW(c0), rj1 = TRD_RAW(c0 + 1);
+        const int ri_r = rb + (lane & 15);
+        const float ri = TRD_RAW(ri_r);
+        const float vj0 = TRD_VFIX(c0, rj0), vj1 = TRD_VFIX(c0 + 1, rj1);
+        const float vi_l = TRD_VFIX(ri_r, ri);
         float rs[16];
         float c0acc = 0.f, c1acc = 0.f;
 #pragma unroll
@@ -273,23 +279,23 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         }
       }
     }
-    // per-CTA partials of p1 = W^T v, p2 = V^T v: the rows of the CTA's row blocks are spread over its 32 warps
-    // (warp w takes row 32 k + w, lane = panel column); all loads of up to 4 blocks are issued before they are used
+    // per-CTA partials of p1 = W^T v, p2 = V^T v: warp w takes row 32 k + w of every owned block (lane = panel column)
     float p1 = 0.f, p2 = 0.f;
     if (P > 0) {
-      for (int k0 = cta; k0 < nrb; k0 += 4 * ncta) {
-        float wv[4], vv[4], rw[4];
+      for (int kp = kfirst; kp < nrb; kp += BP * ncta) {
+        float raw[BP], wv[BP], vv[BP];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = k0 + q * ncta, r = k * 32 + warp;
-          const bool ok = k < nrb && k >= rb_first && r < n && lane < P;
-          rw[q] = (k < nrb && k >= rb_first) ? raw_v(r) : 0.f;
-          wv[q] = ok ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
-          vv[q] = ok ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
+        for (int q = 0; q < BP; ++q) {               // loads of up to BP blocks first ...
+          const int k = kp + q * ncta, r = k * 32 + warp;
+          raw[q] = 0.f; wv[q] = 0.f; vv[q] = 0.f;
+          if (k < nrb && r >= s1 && r < n) {         // warp-uniform
+            raw[q] = TRD_RAW(r);
+            if (lane < P) { wv[q] = __ldcg(mt.Wp + r * NB + lane); vv[q] = __ldcg(mt.Vp + r * NB + lane); }
+          }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float v = vfix((k0 + q * ncta) * 32 + warp, rw[q]);
+        for (int q = 0; q < BP; ++q) {               // ... then their use
+          const float v = TRD_VFIX((kp + q * ncta) * 32 + warp, raw[q]);
           p1 = fmaf(wv[q], v, p1);
           p2 = fmaf(vv[q], v, p2);
         }
@@ -309,107 +315,111 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     group_barrier(mt.bar, epoch, ncta);
     // =========================================================== phase B
     {
-      // ---- every global load of the phase is issued first (they are mutually independent):
-      // (1) the tile partials / panel rows / column entries of the first pass over this CTA's row blocks
-      constexpr int BP = 4;
+      // ---- every global load of the phase is issued before any of them is used (they are mutually independent);
+      // blocks / tile classes without work are skipped by uniform branches
       float* Gs = stage;                               // [BP][32 warps][33]
-      float g[BP][3], vr[BP], wr[BP], ac[BP], rw[BP];
-      auto load_pass = [&](int k0) {
+      float g[BP], vr[BP], wr[BP], ac[BP], rw[BP];
+      int kpass = kfirst;
+      auto load_pass = [&](int kp) {
 #pragma unroll
         for (int q = 0; q < BP; ++q) {
-          const int k = k0 + q * ncta, r = k * 32 + lane;
-          const bool okb = k < nrb && k >= rb_first && r < n;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int X = b0 + warp + 32 * j;
-            g[q][j] = (okb && X < nblk) ? __ldcg(&mt.part[(int64_t)X * np + r]) : 0.f;
+          const int k = kp + q * ncta;
+          g[q] = 0.f; vr[q] = 0.f; wr[q] = 0.f; ac[q] = 0.f; rw[q] = 0.f;
+          if (k < nrb) {                               // uniform
+            const int rl = k * 32 + lane;              // gather: lane = row, warp = tile class
+            if (rl < n) {
+              const float* pp = mt.part + (int64_t)(b0 + warp) * np + rl;
+              float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+              if (b0 + warp < nblk) g0 = __ldcg(pp);
+              if (b0 + warp + 32 < nblk) g1 = __ldcg(pp + (int64_t)32 * np);
+              if (b0 + warp + 64 < nblk) g2 = __ldcg(pp + (int64_t)64 * np);
+              g[q] = (g0 + g1) + g2;
+            }
+            const int r = k * 32 + warp;               // finish: warp = row, lane = panel column
+            if (r >= s1 && r < n) {                    // uniform
+              if (lane < P) { vr[q] = __ldcg(mt.Vp + r * NB + lane); wr[q] = __ldcg(mt.Wp + r * NB + lane); }
+              if (r > s1) ac[q] = __ldcg(A + (int64_t)r * np + s1);
+              rw[q] = TRD_RAW(r);
+            }
           }
         }
-#pragma unroll
-        for (int q = 0; q < BP; ++q) {
-          const int k = k0 + q * ncta, r = k * 32 + warp;
-          const bool okr = k < nrb && k >= rb_first && r >= s + 1 && r < n;
-          vr[q] = (okr && lane < P) ? __ldcg(&mt.Vp[(int64_t)r * NB + lane]) : 0.f;
-          wr[q] = (okr && lane < P) ? __ldcg(&mt.Wp[(int64_t)r * NB + lane]) : 0.f;
-          ac[q] = (okr && r >= s + 2) ? __ldcg(&A[(int64_t)r * np + s + 1]) : 0.f;
-          rw[q] = okr ? raw_v(r) : 0.f;
-        }
       };
-      int k0 = cta;
-      while (k0 < nrb && k0 + (BP - 1) * ncta < rb_first) k0 += BP * ncta;     // first pass with an active block
-      load_pass(k0);
-      // (2) cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
+      load_pass(kpass);
+      // cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
       {
-        float ca[NCP], cb[NCP], cc[NCP];
-        const bool need = warp < P;
+        float sa = 0.f, sb = 0.f, scv = 0.f;
+        if (warp < P) {
+          float ca[NCP], cb[NCP];
 #pragma unroll
-        for (int j = 0; j < NCP; ++j) {
-          const int c = lane + 32 * j;
-          const bool in = c < ncta;
-          ca[j] = (in && need) ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
-          cb[j] = (in && need) ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
-          cc[j] = (in && warp == 0) ? __ldcg(&cpart[64 * ncta + c]) : 0.f;
+          for (int j = 0; j < NCP; ++j) {
+            const int c = lane + 32 * j;
+            ca[j] = c < ncta ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
+            cb[j] = c < ncta ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
+          }
+          sa = sum5(ca); sb = sum5(cb);
         }
-        // (3) row s+1 (warp 1): raw loads now, the rest after the sums are published
-        const int r1 = s + 1;
-        float y1p[3] = {0.f, 0.f, 0.f}, vrow = 0.f, wrow = 0.f, a11 = 0.f;
+        if (warp == 0) {
+          float cc[NCP];
+#pragma unroll
+          for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; cc[j] = c < ncta ? __ldcg(&cpart[64 * ncta + c]) : 0.f; }
+          scv = sum5(cc);
+        }
+        // row s+1 (warp 1): raw loads now, the rest after the sums are published
+        float y1p = 0.f, vrow = 0.f, wrow = 0.f, a11 = 0.f;
         if (warp == 1) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; y1p[j] = X < nblk ? __ldcg(&mt.part[(int64_t)X * np + r1]) : 0.f; }
-          vrow = (lane < P) ? __ldcg(&mt.Vp[(int64_t)r1 * NB + lane]) : 0.f;
-          wrow = (lane < P) ? __ldcg(&mt.Wp[(int64_t)r1 * NB + lane]) : 0.f;
-          a11 = __ldcg(&A[(int64_t)r1 * np + r1]);
+          for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; if (X < nblk) y1p += __ldcg(&mt.part[(int64_t)X * np + s1]); }
+          if (lane < P) { vrow = __ldcg(mt.Vp + s1 * NB + lane); wrow = __ldcg(mt.Wp + s1 * NB + lane); }
+          a11 = __ldcg(&A[(int64_t)s1 * np + s1]);
         }
-        if (need || warp == 0) {
-          const float sa = warp_sum(sum5(ca)), sb = warp_sum(sum5(cb));
-          if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; }
-          if (warp == 0) { const float scv = warp_sum(sum5(cc)); if (lane == 0) sc[64] = scv; }
-        } else if (lane == 0) { sc[warp] = 0.f; sc[32 + warp] = 0.f; }
+        if (warp < P) { sa = warp_sum(sa); sb = warp_sum(sb); }
+        if (warp == 0) scv = warp_sum(scv);
+        if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
         __syncthreads();
         if (warp == 1) {
           const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
           const float ytv1 = sc[64] - 2.f * warp_sum(p1l * p2l);
-          const float y1 = warp_sum((y1p[0] + y1p[1]) + y1p[2] - (vrow * p1l + wrow * p2l));
+          const float y1 = warp_sum(y1p - (vrow * p1l + wrow * p2l));
           const float w1v = tau * (y1 - 0.5f * tau * ytv1);          // v[s+1] = 1
           if (lane == P) { vrow = 1.f; wrow = w1v; }
           s_vrow[lane] = vrow; s_wrow[lane] = wrow;
           const float dd = warp_sum(vrow * wrow);
-          if (lane == 0) { sc[68] = ytv1; sc[69] = w1v; if (cta == 0) mt.d[r1] = a11 - 2.f * dd; }
+          if (lane == 0) { sc[68] = ytv1; sc[69] = w1v; if (cta == 0) mt.d[s1] = a11 - 2.f * dd; }
         }
       }
-      // the gathered partial sums go through shared memory: warp = tile index class, lane = row  ->  lane = class, warp = row
+      // the gathered partial sums go through shared memory: (warp = tile class, lane = row) -> (lane = class, warp = row)
 #pragma unroll
-      for (int q = 0; q < BP; ++q) Gs[(q * 32 + warp) * 33 + lane] = (g[q][0] + g[q][1]) + g[q][2];
+      for (int q = 0; q < BP; ++q) if (kpass + q * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
       __syncthreads();
       const float ytv = sc[68], w1 = sc[69];
       const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
       const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
       float sig = 0.f;
-      for (; k0 < nrb; k0 += BP * ncta) {
+      for (; kpass < nrb; kpass += BP * ncta) {
         // warp w finishes row 32 k + w of each block of the pass (lane = panel column): y, w, x' and its norm partial
 #pragma unroll
         for (int q = 0; q < BP; ++q) {
-          const int k = k0 + q * ncta, r = k * 32 + warp;
-          if (!(k < nrb && k >= rb_first && r >= s + 1 && r < n)) continue;        // warp-uniform
-          const float v = vfix(r, rw[q]);
+          const int k = kpass + q * ncta, r = k * 32 + warp;
+          if (k >= nrb || r < s1 || r >= n) continue;             // warp-uniform
+          const float v = TRD_VFIX(r, rw[q]);
           const float y = warp_sum(Gs[(q * 32 + lane) * 33 + warp] - (vr[q] * p1l + wr[q] * p2l));
           const float xs = warp_sum(vr[q] * wsl + wr[q] * vsl);
           if (lane == 0) {
             const float w = tau * (y - 0.5f * tau * ytv * v);
-            mt.Wp[(int64_t)r * NB + P] = w;
-            mt.Vp[(int64_t)r * NB + P] = v;
-            if (r >= s + 2) {
+            mt.Wp[r * NB + P] = w;
+            mt.Vp[r * NB + P] = v;
+            if (r > s1) {
               const float x = ac[q] - xs - (v * w1 + w);          // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
               col[r] = x;
-              if (r >= s + 3) sig = fmaf(x, x, sig);
+              if (r > s1 + 1) sig = fmaf(x, x, sig);
             }
           }
         }
-        if (k0 + BP * ncta < nrb) {                      // another pass (small groups only): reload, regather
+        if (kpass + BP * ncta < nrb) {                   // another pass (small groups only): reload, regather
           __syncthreads();
-          load_pass(k0 + BP * ncta);
+          load_pass(kpass + BP * ncta);
 #pragma unroll
-          for (int q = 0; q < BP; ++q) Gs[(q * 32 + warp) * 33 + lane] = (g[q][0] + g[q][1]) + g[q][2];
+          for (int q = 0; q < BP; ++q) if (kpass + (BP + q) * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
           __syncthreads();
         }
       }
@@ -423,6 +433,8 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       P += 1;
     }
     group_barrier(mt.bar, epoch, ncta);
+#undef TRD_RAW
+#undef TRD_VFIX
     // =========================================================== rank-2NB update of the lower tiles
     if (P == NB && s < n - 2) {
       const int ub0 = (s + 2) / T;
