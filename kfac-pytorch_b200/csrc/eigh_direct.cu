@@ -131,21 +131,20 @@ void make_layout(const int* n, int count, Layout& L) {
 // averaged over the shrinking trailing matrix)
 // measured on B200 (tests/test_gpu_direct_eigh.py, profiles/): ~10 us of barrier / dependent-load latency per column
 // + 1 ns per row + the tile products
-constexpr double T0 = 9.9e-6, T1 = 1.0e-9, BETA = 2.4e-11;   // per CTA of 512 threads
+constexpr double T0 = 9.9e-6, T1 = 1.0e-9, BETA = 1.2e-11;
 double job_time(int n, int C) { return (double)n * (T0 + T1 * n + BETA * (double)n * n / C); }
 
 void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
   // smallest makespan M such that the CTA-time of all jobs (each sized to finish within M) fits into G * M
   auto ctas_for = [&](int ni, double M) {
     const int nb = (ni + TRD_T - 1) / TRD_T;
-    const int gmax = sytrd_max_group();
-    const int cmin = std::min(gmax, sytrd_min_ctas(ni));
-    const int cmax = std::max(cmin, std::min(gmax, nb * (nb + 1) / 2 / 2 + 1));   // >= 2 tiles per sub-group pays
+    const int cmin = std::min(G, sytrd_min_ctas(ni));
+    const int cmax = std::max(cmin, std::min(G, nb * (nb + 1) / 2 / 2 + 1));   // >= 2 tiles per sub-group pays
     for (int C = cmin; C <= cmax; ++C) if (job_time(ni, C) <= M) return C;
     return cmax;
   };
   double lo = 0, hi = 0;
-  for (int i = 0; i < count; ++i) { lo = std::max(lo, job_time(n[i], sytrd_max_group())); hi += job_time(n[i], 1); }
+  for (int i = 0; i < count; ++i) { lo = std::max(lo, job_time(n[i], G)); hi += job_time(n[i], 1); }
   hi = std::max(hi, lo);
   for (int it = 0; it < 40; ++it) {
     const double M = 0.5 * (lo + hi);
@@ -383,9 +382,8 @@ extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e
   cudaStream_t s = (cudaStream_t)stream;
   const int np = round_up(n, TRD_T), nblk = np / TRD_T;
   const int G = sytrd_max_grid();
-  const int gmax = sytrd_max_group();
-  if (ncta <= 0 || ncta > gmax) ncta = gmax;
-  ncta = std::max(ncta, std::min(gmax, sytrd_min_ctas(n)));
+  if (ncta <= 0 || ncta > G) ncta = G;
+  ncta = std::max(ncta, std::min(G, sytrd_min_ctas(n)));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t oA = take((size_t)np * (np + 128) * 4), oVT = take((size_t)np * np * 4), oVp = take((size_t)np * TRD_NB * 4),

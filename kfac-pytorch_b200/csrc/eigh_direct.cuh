@@ -13,7 +13,7 @@ namespace kfac {
 
 constexpr int TRD_NB = 32;        // panel width (columns per block reflector of the reduction)
 constexpr int TRD_T = 64;         // tile edge of the lower-triangle tiling
-constexpr int TRD_THREADS = 512;  // 16 warps; two CTAs (usually of different matrices) share an SM and hide each other's latency
+constexpr int TRD_THREADS = 1024; // 4 sub-groups of 8 warps
 constexpr int TRD_BT = 128;       // Householder vectors per block reflector of the back-transformation
 constexpr int TRD_CP = 72;        // floats of per-CTA partial scalars: [0,32) W^T v, [32,64) V^T v, 64 v^T A v, 65 |x|^2
 
@@ -38,7 +38,6 @@ struct TrdJob { int mat, cta0, ncta; };
 // all jobs of one launch; a CTA processes the jobs that contain it in list order
 int launch_sytrd(const TrdMat* d_mats, const TrdJob* d_jobs, int njobs, int np_max, int grid, cudaStream_t s);
 int sytrd_max_grid();
-int sytrd_max_group();
 int sytrd_min_ctas(int n);
 
 // ---- divide and conquer (stedc.cu)

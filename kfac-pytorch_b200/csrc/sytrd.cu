@@ -17,16 +17,11 @@
 // is 2/3 n^3 * 4 bytes of L2 reads for the products.  Everything is deterministic (no atomics on data).
 #include "eigh_direct.cuh"
 
-#include <algorithm>
-
 namespace kfac {
 
 namespace {
 
 constexpr int NB = TRD_NB, T = TRD_T;
-constexpr int NW = TRD_THREADS / 32;         // warps per CTA
-constexpr int NSU = NW / 8;                  // update sub-groups (256 threads)
-constexpr int NSP = NW / 4;                  // product sub-groups (128 threads)
 constexpr int UPAD = T + 4;                 // row length of the transposed update staging
 constexpr int SUB_STAGE = 4 * NB * UPAD;    // floats per sub-group: VI^T, WI^T, VJ^T, WJ^T as [NB][UPAD]
 
@@ -124,16 +119,16 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   const int n = mt.n, np = mt.np, nblk = mt.nblk;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sg = warp >> 3;                          // update sub-group (256 threads)
-  const int G = ncta * NSU, sgid = cta * NSU + sg;   // tile owners of the rank-2NB update
+  const int G = ncta * 4, sgid = cta * 4 + sg;       // tile owners of the rank-2NB update
   const int sg8 = warp >> 2, sw4 = warp & 3;         // product sub-group (128 threads) and warp within it
-  const int G8 = ncta * NSP, sgid8 = cta * NSP + sg8;  // tile owners of the symmetric product
-  const int GW = ncta * NW, gw = cta * NW + warp;    // column 0 only: rows r = gw (mod GW)
-  float* stage = smem;                               // NSU * SUB_STAGE (update staging / gather / column partial sums)
-  float* red = stage + NSU * SUB_STAGE;              // NW x 66
-  float* sc = red + NW * 66;                         // 160 scalars: [0,32) p1, [32,64) p2, 64 vAv, 66.. misc, [96,128) vrow, [128,160) wrow
+  const int G8 = ncta * 8, sgid8 = cta * 8 + sg8;    // tile owners of the symmetric product
+  const int GW = ncta * 32, gw = cta * 32 + warp;    // row owners: rows r = gw (mod GW)
+  float* stage = smem;                               // 4 * SUB_STAGE (update staging / column partial sums)
+  float* red = stage + 4 * SUB_STAGE;                // 32 x 66
+  float* sc = red + 32 * 66;                         // 160 scalars: [0,32) p1, [32,64) p2, 64 vAv, 66.. misc, [96,128) vrow, [128,160) wrow
   short2* tlist = reinterpret_cast<short2*>(sc + 160) + sg * MAXT;
-  short2* tlist8 = reinterpret_cast<short2*>(sc + 160) + NSU * MAXT + sg8 * MAXT;
-  __shared__ int s_ntile[NSU + NSP];
+  short2* tlist8 = reinterpret_cast<short2*>(sc + 160) + 4 * MAXT + sg8 * MAXT;
+  __shared__ int s_ntile[12];
   unsigned epoch = 0;
   float* const col = mt.col;
   float* const cpart = mt.cpart;
@@ -160,10 +155,10 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       for (int J = ((sgid8 - tri) % G8 + G8) % G8; J <= I; J += G8)
         if (cnt < MAXT) tlist8[cnt++] = make_short2((short)I, (short)J);
     }
-    s_ntile[NSU + sg8] = cnt;
+    s_ntile[4 + sg8] = cnt;
   }
   __syncthreads();
-  const int ntile = s_ntile[sg], ntile8 = s_ntile[NSU + sg8];
+  const int ntile = s_ntile[sg], ntile8 = s_ntile[4 + sg8];
   int tfirst = 0, tfirst8 = 0;                       // tiles before these indices are dead (I < b0)
 
   // ---- column 0: x = A[1:, 0], |x[1:]|^2 partials, d[0]
@@ -179,7 +174,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     if (lane == 0) red[warp] = sig;
     __syncthreads();
     if (warp == 0) {
-      const float t = warp_sum(lane < NW ? red[lane] : 0.f);
+      const float t = warp_sum(red[lane]);
       if (lane == 0) { cpart[65 * ncta + cta] = t; if (cta == 0) mt.d[0] = __ldcg(&A[0]); }
     }
   }
@@ -193,8 +188,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   float* s_vrow = sc + 96;                           // 32: V[s+1][:]
   float* s_wrow = sc + 128;                          // 32: W[s+1][:]
   const int vt_per = (n + ncta - 1) / ncta, vt_a = cta * vt_per, vt_b = min(n, vt_a + vt_per);
-  constexpr int BP = 2;                              // row blocks per pass
-  constexpr int RH = 32 / NW;                        // rows of a block per warp (warp w takes rows w, w + NW, ...)
+  constexpr int BP = 4;                              // row blocks per pass
   int kfirst = cta;                                  // first owned row block that still has an active row
   for (int s = 0; s <= n - 2; ++s) {
     const int s1 = s + 1;
@@ -289,10 +283,10 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     float p1 = 0.f, p2 = 0.f;
     if (P > 0) {
       for (int kp = kfirst; kp < nrb; kp += BP * ncta) {
-        float raw[BP * RH], wv[BP * RH], vv[BP * RH];
+        float raw[BP], wv[BP], vv[BP];
 #pragma unroll
-        for (int q = 0; q < BP * RH; ++q) {          // loads of up to BP blocks first ...
-          const int k = kp + (q / RH) * ncta, r = k * 32 + warp + (q % RH) * NW;
+        for (int q = 0; q < BP; ++q) {               // loads of up to BP blocks first ...
+          const int k = kp + q * ncta, r = k * 32 + warp;
           raw[q] = 0.f; wv[q] = 0.f; vv[q] = 0.f;
           if (k < nrb && r >= s1 && r < n) {         // warp-uniform
             raw[q] = TRD_RAW(r);
@@ -300,8 +294,8 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
           }
         }
 #pragma unroll
-        for (int q = 0; q < BP * RH; ++q) {          // ... then their use
-          const float v = TRD_VFIX((kp + (q / RH) * ncta) * 32 + warp + (q % RH) * NW, raw[q]);
+        for (int q = 0; q < BP; ++q) {               // ... then their use
+          const float v = TRD_VFIX((kp + q * ncta) * 32 + warp, raw[q]);
           p1 = fmaf(wv[q], v, p1);
           p2 = fmaf(vv[q], v, p2);
         }
@@ -315,7 +309,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     if (tid < 65) {
       float t = 0.f;
 #pragma unroll 8
-      for (int w = 0; w < NW; ++w) t += red[w * 66 + tid];
+      for (int w = 0; w < 32; ++w) t += red[w * 66 + tid];
       cpart[tid * ncta + cta] = t;
     }
     group_barrier(mt.bar, epoch, ncta);
@@ -323,58 +317,46 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     {
       // ---- every global load of the phase is issued before any of them is used (they are mutually independent);
       // blocks / tile classes without work are skipped by uniform branches
-      float* Gs = stage;                               // [BP][NW tile classes][33]
-      constexpr int NJ = 5;                            // tile classes per warp covered without a loop (nblk <= NJ * NW)
-      float g[BP], vr[BP * RH], wr[BP * RH], ac[BP * RH], rw[BP * RH];
+      float* Gs = stage;                               // [BP][32 warps][33]
+      float g[BP], vr[BP], wr[BP], ac[BP], rw[BP];
       int kpass = kfirst;
       auto load_pass = [&](int kp) {
 #pragma unroll
         for (int q = 0; q < BP; ++q) {
           const int k = kp + q * ncta;
-          g[q] = 0.f;
-#pragma unroll
-          for (int h = 0; h < RH; ++h) { vr[q * RH + h] = 0.f; wr[q * RH + h] = 0.f; ac[q * RH + h] = 0.f; rw[q * RH + h] = 0.f; }
+          g[q] = 0.f; vr[q] = 0.f; wr[q] = 0.f; ac[q] = 0.f; rw[q] = 0.f;
           if (k < nrb) {                               // uniform
             const int rl = k * 32 + lane;              // gather: lane = row, warp = tile class
             if (rl < n) {
               const float* pp = mt.part + (int64_t)(b0 + warp) * np + rl;
-              float t[NJ];
-#pragma unroll
-              for (int j = 0; j < NJ; ++j) t[j] = (b0 + warp + NW * j < nblk) ? __ldcg(pp + (int64_t)(NW * j) * np) : 0.f;
-              float acc = ((t[0] + t[1]) + (t[2] + t[3])) + t[4];
-              for (int X = b0 + warp + NW * NJ; X < nblk; X += NW) acc += __ldcg(mt.part + (int64_t)X * np + rl);
-              g[q] = acc;
+              float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+              if (b0 + warp < nblk) g0 = __ldcg(pp);
+              if (b0 + warp + 32 < nblk) g1 = __ldcg(pp + (int64_t)32 * np);
+              if (b0 + warp + 64 < nblk) g2 = __ldcg(pp + (int64_t)64 * np);
+              g[q] = (g0 + g1) + g2;
             }
-#pragma unroll
-            for (int h = 0; h < RH; ++h) {
-              const int r = k * 32 + warp + h * NW;    // finish: warp = row, lane = panel column
-              if (r >= s1 && r < n) {                  // uniform
-                if (lane < P) { vr[q * RH + h] = __ldcg(mt.Vp + r * NB + lane); wr[q * RH + h] = __ldcg(mt.Wp + r * NB + lane); }
-                if (r > s1) ac[q * RH + h] = __ldcg(A + (int64_t)r * np + s1);
-                rw[q * RH + h] = TRD_RAW(r);
-              }
+            const int r = k * 32 + warp;               // finish: warp = row, lane = panel column
+            if (r >= s1 && r < n) {                    // uniform
+              if (lane < P) { vr[q] = __ldcg(mt.Vp + r * NB + lane); wr[q] = __ldcg(mt.Wp + r * NB + lane); }
+              if (r > s1) ac[q] = __ldcg(A + (int64_t)r * np + s1);
+              rw[q] = TRD_RAW(r);
             }
           }
         }
       };
       load_pass(kpass);
-      // cross-CTA sums of p1, p2, vAv: warp w owns outputs w + NW h (p1), 32 + w + NW h (p2) and (warp 0) 64
+      // cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
       {
-        float sa[RH], sb[RH], scv = 0.f;
+        float sa = 0.f, sb = 0.f, scv = 0.f;
+        if (warp < P) {
+          float ca[NCP], cb[NCP];
 #pragma unroll
-        for (int h = 0; h < RH; ++h) {
-          sa[h] = 0.f; sb[h] = 0.f;
-          const int o = warp + h * NW;
-          if (o < P) {
-            float ca[NCP], cb[NCP];
-#pragma unroll
-            for (int j = 0; j < NCP; ++j) {
-              const int c = lane + 32 * j;
-              ca[j] = c < ncta ? __ldcg(&cpart[o * ncta + c]) : 0.f;
-              cb[j] = c < ncta ? __ldcg(&cpart[(32 + o) * ncta + c]) : 0.f;
-            }
-            sa[h] = sum5(ca); sb[h] = sum5(cb);
+          for (int j = 0; j < NCP; ++j) {
+            const int c = lane + 32 * j;
+            ca[j] = c < ncta ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
+            cb[j] = c < ncta ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
           }
+          sa = sum5(ca); sb = sum5(cb);
         }
         if (warp == 0) {
           float cc[NCP];
@@ -385,17 +367,14 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         // row s+1 (warp 1): raw loads now, the rest after the sums are published
         float y1p = 0.f, vrow = 0.f, wrow = 0.f, a11 = 0.f;
         if (warp == 1) {
-          for (int X = b0 + lane; X < nblk; X += 32) y1p += __ldcg(&mt.part[(int64_t)X * np + s1]);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; if (X < nblk) y1p += __ldcg(&mt.part[(int64_t)X * np + s1]); }
           if (lane < P) { vrow = __ldcg(mt.Vp + s1 * NB + lane); wrow = __ldcg(mt.Wp + s1 * NB + lane); }
           a11 = __ldcg(&A[(int64_t)s1 * np + s1]);
         }
-#pragma unroll
-        for (int h = 0; h < RH; ++h) {
-          const int o = warp + h * NW;
-          if (o < P) { sa[h] = warp_sum(sa[h]); sb[h] = warp_sum(sb[h]); }
-          if (lane == 0) { sc[o] = sa[h]; sc[32 + o] = sb[h]; }
-        }
-        if (warp == 0) { scv = warp_sum(scv); if (lane == 0) sc[64] = scv; }
+        if (warp < P) { sa = warp_sum(sa); sb = warp_sum(sb); }
+        if (warp == 0) scv = warp_sum(scv);
+        if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
         __syncthreads();
         if (warp == 1) {
           const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
@@ -410,21 +389,20 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       }
       // the gathered partial sums go through shared memory: (warp = tile class, lane = row) -> (lane = class, warp = row)
 #pragma unroll
-      for (int q = 0; q < BP; ++q) if (kpass + q * ncta < nrb) Gs[(q * NW + warp) * 33 + lane] = g[q];
+      for (int q = 0; q < BP; ++q) if (kpass + q * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
       __syncthreads();
       const float ytv = sc[68], w1 = sc[69];
       const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
       const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
       float sig = 0.f;
       for (; kpass < nrb; kpass += BP * ncta) {
-        // warp w finishes rows 32 k + w + NW h of each block of the pass (lane = panel column): y, w, x', norm partial
+        // warp w finishes row 32 k + w of each block of the pass (lane = panel column): y, w, x' and its norm partial
 #pragma unroll
-        for (int q = 0; q < BP * RH; ++q) {
-          const int k = kpass + (q / RH) * ncta, rloc = warp + (q % RH) * NW, r = k * 32 + rloc;
+        for (int q = 0; q < BP; ++q) {
+          const int k = kpass + q * ncta, r = k * 32 + warp;
           if (k >= nrb || r < s1 || r >= n) continue;             // warp-uniform
           const float v = TRD_VFIX(r, rw[q]);
-          const float gsum = (lane < NW) ? Gs[((q / RH) * NW + lane) * 33 + rloc] : 0.f;
-          const float y = warp_sum(gsum - (vr[q] * p1l + wr[q] * p2l));
+          const float y = warp_sum(Gs[(q * 32 + lane) * 33 + warp] - (vr[q] * p1l + wr[q] * p2l));
           const float xs = warp_sum(vr[q] * wsl + wr[q] * vsl);
           if (lane == 0) {
             const float w = tau * (y - 0.5f * tau * ytv * v);
@@ -441,7 +419,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
           __syncthreads();
           load_pass(kpass + BP * ncta);
 #pragma unroll
-          for (int q = 0; q < BP; ++q) if (kpass + (BP + q) * ncta < nrb) Gs[(q * NW + warp) * 33 + lane] = g[q];
+          for (int q = 0; q < BP; ++q) if (kpass + (BP + q) * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
           __syncthreads();
         }
       }
@@ -449,7 +427,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       if (lane == 0) red[warp] = sig;
       __syncthreads();
       if (warp == 0) {
-        const float t = warp_sum(lane < NW ? red[lane] : 0.f);
+        const float t = warp_sum(red[lane]);
         if (lane == 0) cpart[65 * ncta + cta] = t;
       }
       P += 1;
@@ -516,7 +494,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   if (cta == 0 && tid == 0) { mt.e[n - 1] = 0.f; mt.tau[n - 1] = 0.f; }
 }
 
-__global__ void __launch_bounds__(TRD_THREADS, 2) sytrd_kernel(const TrdMat* mats, const TrdJob* jobs, int njobs) {
+__global__ void __launch_bounds__(TRD_THREADS, 1) sytrd_kernel(const TrdMat* mats, const TrdJob* jobs, int njobs) {
   extern __shared__ __align__(16) float trd_smem[];
   for (int j = 0; j < njobs; ++j) {
     const TrdJob job = jobs[j];
@@ -528,33 +506,19 @@ __global__ void __launch_bounds__(TRD_THREADS, 2) sytrd_kernel(const TrdMat* mat
 }
 
 size_t trd_smem_bytes(int) {
-  return sizeof(float) * ((size_t)NSU * SUB_STAGE + NW * 66 + 160) + sizeof(short2) * (NSU + NSP) * MAXT + 64;
+  return sizeof(float) * ((size_t)4 * SUB_STAGE + 32 * 66 + 160) + sizeof(short2) * 12 * MAXT + 64;
 }
 
 }  // namespace
 
-// cooperative grid: as many CTAs as are co-resident (two per SM when registers / shared memory allow)
-int sytrd_max_grid() {
-  static int grid = 0;
-  if (!grid) {
-    int per_sm = 1;
-    const size_t smem = trd_smem_bytes(0);
-    cudaFuncSetAttribute(sytrd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sytrd_kernel, TRD_THREADS, smem) != cudaSuccess || per_sm < 1)
-      per_sm = 1;
-    grid = std::min(per_sm, 2) * tc_num_sms();
-  }
-  return grid;
-}
-// largest CTA group of one matrix (the cross-CTA reductions read NCP x 32 partials per lane)
-int sytrd_max_group() { return std::min(sytrd_max_grid(), std::min(NCP * 32, tc_num_sms())); }
+int sytrd_max_grid() { return tc_num_sms(); }
 
 // smallest group that can own all lower tiles of an n x n matrix (tile list of MAXT entries per sub-group)
 int sytrd_min_ctas(int n) {
   const int nblk = (n + T - 1) / T, tiles = nblk * (nblk + 1) / 2;
   if (nblk >= MAXT) return 1 << 30;
   int C = 1;
-  while (tiles / (NSU * C) + nblk + 1 > MAXT) ++C;
+  while (tiles / (4 * C) + nblk + 1 > MAXT) ++C;
   return C;
 }
 
