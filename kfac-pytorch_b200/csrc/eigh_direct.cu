@@ -131,7 +131,7 @@ void make_layout(const int* n, int count, Layout& L) {
 // averaged over the shrinking trailing matrix)
 // measured on B200 (tests/test_gpu_direct_eigh.py, profiles/): ~10 us of barrier / dependent-load latency per column
 // + 1 ns per row + the tile products
-constexpr double T0 = 9.9e-6, T1 = 1.0e-9, BETA = 1.2e-11;
+constexpr double T0 = 8.7e-6, T1 = 4.2e-10, BETA = 1.9e-11;
 double job_time(int n, int C) { return (double)n * (T0 + T1 * n + BETA * (double)n * n / C); }
 
 void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
@@ -260,6 +260,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)m.np * TRD_NB * 4, s));
     KFAC_CUDA(cudaMemsetAsync(t.Wp, 0, (size_t)m.np * TRD_NB * 4, s));
     KFAC_CUDA(cudaMemsetAsync(t.bar, 0, 256, s));
+    KFAC_CUDA(cudaMemsetAsync(t.cpart, 0, (size_t)G * TRD_CP * 4, s));     // (epoch, value) slots: epoch 0 = nothing published
   }
   std::vector<TrdJob> jobs;
   make_schedule(ns.data(), count, G, jobs);
@@ -403,6 +404,7 @@ extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e
   KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)np * TRD_NB * 4, s));
   KFAC_CUDA(cudaMemsetAsync(t.Wp, 0, (size_t)np * TRD_NB * 4, s));
   KFAC_CUDA(cudaMemsetAsync(t.bar, 0, 256, s));
+  KFAC_CUDA(cudaMemsetAsync(t.cpart, 0, (size_t)G * TRD_CP * 4, s));
   TrdJob job{0, 0, ncta};
   KFAC_CUDA(cudaMemcpyAsync(base + oMat, &t, sizeof(t), cudaMemcpyHostToDevice, s));
   KFAC_CUDA(cudaMemcpyAsync(base + oJob, &job, sizeof(job), cudaMemcpyHostToDevice, s));
@@ -448,3 +450,6 @@ extern "C" size_t kfac_experimental_direct_workspace_bytes(int n) {
   const int np = (n + 63) / 64 * 64;
   return (size_t)np * np * 4 * 4 + (size_t)np * 4096 + (1u << 22);
 }
+
+namespace kfac { int sytrd_profile(int on, unsigned long long* out16); }
+extern "C" int kfac_experimental_sytrd_profile(int on, unsigned long long* out16) { return kfac::sytrd_profile(on, out16); }

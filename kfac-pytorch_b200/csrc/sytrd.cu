@@ -31,6 +31,37 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 
+// flagged 64-bit slots (epoch << 32 | float bits): data and arrival flag in one word
+__device__ __forceinline__ void slot_store(unsigned long long* p, unsigned epoch, float v) {
+  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long slot_load(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+// sum over the CTAs of slot row `row` once every CTA has published epoch `epoch` (whole warp; lanes take ctas lane, lane+32, ..)
+__device__ __forceinline__ float slot_sum(const unsigned long long* slots, int row, int ncta, unsigned epoch, int lane) {
+  const unsigned long long* p = slots + (size_t)row * ncta;
+  unsigned long long w[5];
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {                  // groups have at most 160 CTAs
+      const int c = lane + 32 * j;
+      w[j] = c < ncta ? slot_load(p + c) : ((unsigned long long)epoch << 32);
+      ok = ok && ((unsigned)(w[j] >> 32) == epoch);
+    }
+    if (ok) break;
+  }
+  float acc = ((__uint_as_float((unsigned)w[0]) + __uint_as_float((unsigned)w[1])) +
+               (__uint_as_float((unsigned)w[2]) + __uint_as_float((unsigned)w[3]))) + __uint_as_float((unsigned)w[4]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
 __device__ __forceinline__ void group_barrier(unsigned* bar, unsigned& epoch, int ncta) {
   __syncthreads();
   if (ncta > 1) {
@@ -58,6 +89,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// optional phase timing (CTA 0, thread 0 of every group accumulates clock64 deltas): set by kfac_experimental_sytrd_profile
+__device__ unsigned long long g_trd_prof[16];
+__device__ int g_trd_prof_on = 0;
+#define TRD_STAMP(i) do { if (prof) { const long long t__ = clock64(); if (tid == 0) atomicAdd(&g_trd_prof[i], (unsigned long long)(t__ - tprev)); tprev = t__; } } while (0)
 
 constexpr int MAXT = 256;                   // owned tiles per sub-group (list in shared memory)
 constexpr int NCP = 5;                      // ceil(max CTAs per group / 32)
@@ -131,35 +167,33 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   __shared__ int s_ntile[12];
   unsigned epoch = 0;
   float* const col = mt.col;
-  float* const cpart = mt.cpart;
+  unsigned long long* const slots = reinterpret_cast<unsigned long long*>(mt.cpart);
   const float* __restrict__ A = mt.A;
 
   if (n == 1) {
     if (cta == 0 && tid == 0) { mt.d[0] = mt.A[0]; mt.tau[0] = 0.f; mt.e[0] = 0.f; }
     return;
   }
-  // static tile ownership: tile (I, J), I >= J, belongs to sub-group (I (I + 1) / 2 + J) mod G
-  if ((tid & 255) == 0) {
+  // static tile ownership.  Tiles are numbered by decreasing column block J (t = 0: (nblk-1, nblk-1); then the two
+  // tiles of column nblk-2; ...) and dealt round-robin to the sub-groups: the tiles still active at step s
+  // (J >= b0) are a PREFIX of that numbering, so every sub-group holds the same number of active tiles (+-1) at every
+  // step, and its list needs no scan for dead entries.
+  auto build_list = [&](short2* list, int first, int stride) {
+    const int tiles = nblk * (nblk + 1) / 2;
     int cnt = 0;
-    for (int I = 0; I < nblk; ++I) {
-      const int tri = (int)(((int64_t)I * (I + 1) / 2) % G);
-      for (int J = ((sgid - tri) % G + G) % G; J <= I; J += G)
-        if (cnt < MAXT) tlist[cnt++] = make_short2((short)I, (short)J);
+    for (int t = first; t < tiles && cnt < MAXT; t += stride) {
+      int j = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+      while ((j + 1) * (j + 2) / 2 <= t) ++j;
+      while (j * (j + 1) / 2 > t) --j;
+      const int J = nblk - 1 - j, I = J + (t - j * (j + 1) / 2);
+      list[cnt++] = make_short2((short)I, (short)J);
     }
-    s_ntile[sg] = cnt;
-  }
-  if ((tid & 127) == 0) {
-    int cnt = 0;
-    for (int I = 0; I < nblk; ++I) {
-      const int tri = (int)(((int64_t)I * (I + 1) / 2) % G8);
-      for (int J = ((sgid8 - tri) % G8 + G8) % G8; J <= I; J += G8)
-        if (cnt < MAXT) tlist8[cnt++] = make_short2((short)I, (short)J);
-    }
-    s_ntile[4 + sg8] = cnt;
-  }
+    return cnt;
+  };
+  if ((tid & 255) == 0) s_ntile[sg] = build_list(tlist, sgid, G);
+  if ((tid & 127) == 0) s_ntile[4 + sg8] = build_list(tlist8, sgid8, G8);
   __syncthreads();
   const int ntile = s_ntile[sg], ntile8 = s_ntile[4 + sg8];
-  int tfirst = 0, tfirst8 = 0;                       // tiles before these indices are dead (I < b0)
 
   // ---- column 0: x = A[1:, 0], |x[1:]|^2 partials, d[0]
   {
@@ -175,12 +209,13 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     __syncthreads();
     if (warp == 0) {
       const float t = warp_sum(red[lane]);
-      if (lane == 0) { cpart[65 * ncta + cta] = t; if (cta == 0) mt.d[0] = __ldcg(&A[0]); }
+      if (lane == 0) { slot_store(&slots[65 * ncta + cta], 1u, t); if (cta == 0) mt.d[0] = __ldcg(&A[0]); }
     }
   }
-  group_barrier(mt.bar, epoch, ncta);
 
   int P = 0;                                         // columns in the current panel
+  const bool prof = g_trd_prof_on != 0 && cta == 0;
+  long long tprev = prof ? clock64() : 0;
   // Vector work is organised in ROW BLOCKS of 32 consecutive rows; block k belongs to CTA (k mod ncta) and its rows
   // are spread over the CTA's 32 warps (warp w takes row 32 k + w).  Code paths without work are skipped by
   // WARP-UNIFORM branches (the kernel is instruction-issue bound, not bandwidth bound).
@@ -193,16 +228,13 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   for (int s = 0; s <= n - 2; ++s) {
     const int s1 = s + 1;
     const int b0 = s1 / T, rb_first = s1 / 32;
-    while (tfirst < ntile && tlist[tfirst].x < b0) ++tfirst;
-    while (tfirst8 < ntile8 && tlist8[tfirst8].x < b0) ++tfirst8;
     while (kfirst < rb_first) kfirst += ncta;
     // =========================================================== phase C: Householder scalars (warp 0)
+    // (the |x|^2 partials carry the arrival flags of the previous phase: polling them IS the group barrier; `col`
+    // and the panel columns written before the partials are visible once all of them have arrived)
     if (warp == 0) {
-      float sgp[NCP];
-#pragma unroll
-      for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; sgp[j] = c < ncta ? __ldcg(&cpart[65 * ncta + c]) : 0.f; }
+      const float sigma = slot_sum(slots, 65, ncta, (unsigned)(s + 1), lane);
       const float alpha = __ldcg(&col[s1]);
-      const float sigma = warp_sum(sum5(sgp));
       if (lane == 0) {
         float beta, tau, scal;
         if (sigma == 0.f) { beta = alpha; tau = 0.f; scal = 0.f; }
@@ -216,234 +248,16 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       }
     }
     __syncthreads();
-    const float tau = sc[66], scal = sc[67];
-    // v[r] = 0 (r <= s), 1 (r = s + 1), x[r] * scal (r > s + 1): x is read straight from `col`
-#define TRD_RAW(r) (((r) > s1 && (r) < n) ? __ldcg(col + (r)) : 0.f)
-#define TRD_VFIX(r, raw) ((r) == s1 ? 1.f : (raw) * scal)
-    // =========================================================== phase A
-    // the Householder vector is kept for the back-transformation (each CTA writes a slice of the row)
-    if (vt_a + tid < vt_b) {
-      float* vt = mt.VT + (int64_t)s * mt.ldv;
-      float* vb = mt.Vb ? mt.Vb + (int64_t)(s / TRD_BT) * np * TRD_BT + (s % TRD_BT) : nullptr;
-      for (int r = vt_a + tid; r < vt_b; r += TRD_THREADS) {
-        const float raw = TRD_RAW(r);
-        const float v = TRD_VFIX(r, raw);
-        vt[r] = v;
-        if (vb) vb[(int64_t)r * TRD_BT] = v;
-      }
-    }
-    // symmetric product with the lower tiles of this sub-group (128 threads: a warp takes 16 rows of the tile)
-    float vav = 0.f;
-    {
-      float* cs = stage + sg8 * (4 * T);             // column partial sums: [4 warps][64]
-      const int st_tid = tid & 127;
-      for (int ti = tfirst8; ti < ntile8; ++ti) {
-        const int I = tlist8[ti].x, J = tlist8[ti].y;
-        if (J < b0) continue;
-        const int rb = I * T + sw4 * 16, c0 = J * T + 2 * lane;
-        const float* ap = A + (int64_t)rb * np + c0;
-        float2 a[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(ap + (int64_t)k * np));
-        const float rj0 = TRD_RAW(c0), rj1 = TRD_RAW(c0 + 1);
-        const int ri_r = rb + (lane & 15);
-        const float ri = TRD_RAW(ri_r);
-        const float vj0 = TRD_VFIX(c0, rj0), vj1 = TRD_VFIX(c0 + 1, rj1);
-        const float vi_l = TRD_VFIX(ri_r, ri);
-        float rs[16];
-        float c0acc = 0.f, c1acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float vi = __shfl_sync(0xffffffffu, vi_l, k);
-          rs[k] = fmaf(a[k].x, vj0, a[k].y * vj1);
-          c0acc = fmaf(a[k].x, vi, c0acc);
-          c1acc = fmaf(a[k].y, vi, c1acc);
-        }
-        const float tot = reduce16(rs, lane);
-        const int rid = (lane >> 1) & 15;
-        const float vi_r = __shfl_sync(0xffffffffu, vi_l, rid);
-        if ((lane & 1) == 0) {
-          mt.part[(int64_t)J * np + rb + rid] = tot;
-          const float t = tot * vi_r;
-          vav += (I == J) ? t : 2.f * t;
-        }
-        if (I != J) {
-          sub_sync8(sg8);                            // previous tile's readers are done with cs
-          cs[sw4 * T + 2 * lane] = c0acc;
-          cs[sw4 * T + 2 * lane + 1] = c1acc;
-          sub_sync8(sg8);
-          if (st_tid < T) {
-            const float t = (cs[st_tid] + cs[T + st_tid]) + (cs[2 * T + st_tid] + cs[3 * T + st_tid]);
-            mt.part[(int64_t)I * np + J * T + st_tid] = t;
-          }
-        }
-      }
-    }
-    // per-CTA partials of p1 = W^T v, p2 = V^T v: warp w takes row 32 k + w of every owned block (lane = panel column)
-    float p1 = 0.f, p2 = 0.f;
-    if (P > 0) {
-      for (int kp = kfirst; kp < nrb; kp += BP * ncta) {
-        float raw[BP], wv[BP], vv[BP];
-#pragma unroll
-        for (int q = 0; q < BP; ++q) {               // loads of up to BP blocks first ...
-          const int k = kp + q * ncta, r = k * 32 + warp;
-          raw[q] = 0.f; wv[q] = 0.f; vv[q] = 0.f;
-          if (k < nrb && r >= s1 && r < n) {         // warp-uniform
-            raw[q] = TRD_RAW(r);
-            if (lane < P) { wv[q] = __ldcg(mt.Wp + r * NB + lane); vv[q] = __ldcg(mt.Vp + r * NB + lane); }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < BP; ++q) {               // ... then their use
-          const float v = TRD_VFIX((kp + q * ncta) * 32 + warp, raw[q]);
-          p1 = fmaf(wv[q], v, p1);
-          p2 = fmaf(vv[q], v, p2);
-        }
-      }
-    }
-    vav = warp_sum(vav);
-    red[warp * 66 + lane] = p1;
-    red[warp * 66 + 32 + lane] = p2;
-    if (lane == 0) red[warp * 66 + 64] = vav;
-    __syncthreads();
-    if (tid < 65) {
-      float t = 0.f;
-#pragma unroll 8
-      for (int w = 0; w < 32; ++w) t += red[w * 66 + tid];
-      cpart[tid * ncta + cta] = t;
-    }
-    group_barrier(mt.bar, epoch, ncta);
-    // =========================================================== phase B
-    {
-      // ---- every global load of the phase is issued before any of them is used (they are mutually independent);
-      // blocks / tile classes without work are skipped by uniform branches
-      float* Gs = stage;                               // [BP][32 warps][33]
-      float g[BP], vr[BP], wr[BP], ac[BP], rw[BP];
-      int kpass = kfirst;
-      auto load_pass = [&](int kp) {
-#pragma unroll
-        for (int q = 0; q < BP; ++q) {
-          const int k = kp + q * ncta;
-          g[q] = 0.f; vr[q] = 0.f; wr[q] = 0.f; ac[q] = 0.f; rw[q] = 0.f;
-          if (k < nrb) {                               // uniform
-            const int rl = k * 32 + lane;              // gather: lane = row, warp = tile class
-            if (rl < n) {
-              const float* pp = mt.part + (int64_t)(b0 + warp) * np + rl;
-              float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-              if (b0 + warp < nblk) g0 = __ldcg(pp);
-              if (b0 + warp + 32 < nblk) g1 = __ldcg(pp + (int64_t)32 * np);
-              if (b0 + warp + 64 < nblk) g2 = __ldcg(pp + (int64_t)64 * np);
-              g[q] = (g0 + g1) + g2;
-            }
-            const int r = k * 32 + warp;               // finish: warp = row, lane = panel column
-            if (r >= s1 && r < n) {                    // uniform
-              if (lane < P) { vr[q] = __ldcg(mt.Vp + r * NB + lane); wr[q] = __ldcg(mt.Wp + r * NB + lane); }
-              if (r > s1) ac[q] = __ldcg(A + (int64_t)r * np + s1);
-              rw[q] = TRD_RAW(r);
-            }
-          }
-        }
-      };
-      load_pass(kpass);
-      // cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
-      {
-        float sa = 0.f, sb = 0.f, scv = 0.f;
-        if (warp < P) {
-          float ca[NCP], cb[NCP];
-#pragma unroll
-          for (int j = 0; j < NCP; ++j) {
-            const int c = lane + 32 * j;
-            ca[j] = c < ncta ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
-            cb[j] = c < ncta ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
-          }
-          sa = sum5(ca); sb = sum5(cb);
-        }
-        if (warp == 0) {
-          float cc[NCP];
-#pragma unroll
-          for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; cc[j] = c < ncta ? __ldcg(&cpart[64 * ncta + c]) : 0.f; }
-          scv = sum5(cc);
-        }
-        // row s+1 (warp 1): raw loads now, the rest after the sums are published
-        float y1p = 0.f, vrow = 0.f, wrow = 0.f, a11 = 0.f;
-        if (warp == 1) {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; if (X < nblk) y1p += __ldcg(&mt.part[(int64_t)X * np + s1]); }
-          if (lane < P) { vrow = __ldcg(mt.Vp + s1 * NB + lane); wrow = __ldcg(mt.Wp + s1 * NB + lane); }
-          a11 = __ldcg(&A[(int64_t)s1 * np + s1]);
-        }
-        if (warp < P) { sa = warp_sum(sa); sb = warp_sum(sb); }
-        if (warp == 0) scv = warp_sum(scv);
-        if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
-        __syncthreads();
-        if (warp == 1) {
-          const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
-          const float ytv1 = sc[64] - 2.f * warp_sum(p1l * p2l);
-          const float y1 = warp_sum(y1p - (vrow * p1l + wrow * p2l));
-          const float w1v = tau * (y1 - 0.5f * tau * ytv1);          // v[s+1] = 1
-          if (lane == P) { vrow = 1.f; wrow = w1v; }
-          s_vrow[lane] = vrow; s_wrow[lane] = wrow;
-          const float dd = warp_sum(vrow * wrow);
-          if (lane == 0) { sc[68] = ytv1; sc[69] = w1v; if (cta == 0) mt.d[s1] = a11 - 2.f * dd; }
-        }
-      }
-      // the gathered partial sums go through shared memory: (warp = tile class, lane = row) -> (lane = class, warp = row)
-#pragma unroll
-      for (int q = 0; q < BP; ++q) if (kpass + q * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
-      __syncthreads();
-      const float ytv = sc[68], w1 = sc[69];
-      const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
-      const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
-      float sig = 0.f;
-      for (; kpass < nrb; kpass += BP * ncta) {
-        // warp w finishes row 32 k + w of each block of the pass (lane = panel column): y, w, x' and its norm partial
-#pragma unroll
-        for (int q = 0; q < BP; ++q) {
-          const int k = kpass + q * ncta, r = k * 32 + warp;
-          if (k >= nrb || r < s1 || r >= n) continue;             // warp-uniform
-          const float v = TRD_VFIX(r, rw[q]);
-          const float y = warp_sum(Gs[(q * 32 + lane) * 33 + warp] - (vr[q] * p1l + wr[q] * p2l));
-          const float xs = warp_sum(vr[q] * wsl + wr[q] * vsl);
-          if (lane == 0) {
-            const float w = tau * (y - 0.5f * tau * ytv * v);
-            mt.Wp[r * NB + P] = w;
-            mt.Vp[r * NB + P] = v;
-            if (r > s1) {
-              const float x = ac[q] - xs - (v * w1 + w);          // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
-              col[r] = x;
-              if (r > s1 + 1) sig = fmaf(x, x, sig);
-            }
-          }
-        }
-        if (kpass + BP * ncta < nrb) {                   // another pass (small groups only): reload, regather
-          __syncthreads();
-          load_pass(kpass + BP * ncta);
-#pragma unroll
-          for (int q = 0; q < BP; ++q) if (kpass + (BP + q) * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
-          __syncthreads();
-        }
-      }
-      sig = warp_sum(sig);
-      if (lane == 0) red[warp] = sig;
-      __syncthreads();
-      if (warp == 0) {
-        const float t = warp_sum(red[lane]);
-        if (lane == 0) cpart[65 * ncta + cta] = t;
-      }
-      P += 1;
-    }
-    group_barrier(mt.bar, epoch, ncta);
-#undef TRD_RAW
-#undef TRD_VFIX
+    TRD_STAMP(0);      // phase C (scalars)
     // =========================================================== rank-2NB update of the lower tiles
-    if (P == NB && s < n - 2) {
-      const int ub0 = (s + 2) / T;
+    if (P == NB) {                                     // (every CTA has published its panel column: see phase C)
+      const int ub0 = b0;
       float* st = stage + sg * SUB_STAGE;
       float* VIt = st, *WIt = st + NB * UPAD, *VJt = st + 2 * NB * UPAD, *WJt = st + 3 * NB * UPAD;
       const int st_tid = tid & 255;
-      for (int ti = tfirst; ti < ntile; ++ti) {
+      for (int ti = 0; ti < ntile; ++ti) {
         const int I = tlist[ti].x, J = tlist[ti].y;
-        if (I < ub0 || J < ub0) continue;            // uniform within the sub-group
+        if (J < ub0) break;                          // uniform within the sub-group: the active tiles are a prefix
         sub_sync(sg);
         // stage the four 64 x NB operand blocks transposed ([k][row])
 #pragma unroll
@@ -488,8 +302,227 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         }
       }
       P = 0;
+      TRD_STAMP(8);    // rank-2NB update
       group_barrier(mt.bar, epoch, ncta);
+      TRD_STAMP(9);    // barrier 3
     }
+    const float tau = sc[66], scal = sc[67];
+    // v[r] = 0 (r <= s), 1 (r = s + 1), x[r] * scal (r > s + 1): x is read straight from `col`
+#define TRD_RAW(r) (((r) > s1 && (r) < n) ? __ldcg(col + (r)) : 0.f)
+#define TRD_VFIX(r, raw) ((r) == s1 ? 1.f : (raw) * scal)
+    // =========================================================== phase A
+    // the Householder vector is kept for the back-transformation (each CTA writes a slice of the row)
+    if (vt_a + tid < vt_b) {
+      float* vt = mt.VT + (int64_t)s * mt.ldv;
+      float* vb = mt.Vb ? mt.Vb + (int64_t)(s / TRD_BT) * np * TRD_BT + (s % TRD_BT) : nullptr;
+      for (int r = vt_a + tid; r < vt_b; r += TRD_THREADS) {
+        const float raw = TRD_RAW(r);
+        const float v = TRD_VFIX(r, raw);
+        vt[r] = v;
+        if (vb) vb[(int64_t)r * TRD_BT] = v;
+      }
+    }
+    // symmetric product with the lower tiles of this sub-group (128 threads: a warp takes 16 rows of the tile)
+    float vav = 0.f;
+    {
+      float* cs = stage + sg8 * (4 * T);             // column partial sums: [4 warps][64]
+      const int st_tid = tid & 127;
+      for (int ti = 0; ti < ntile8; ++ti) {
+        const int I = tlist8[ti].x, J = tlist8[ti].y;
+        if (J < b0) break;                           // the active tiles are a prefix of the list
+        const int rb = I * T + sw4 * 16, c0 = J * T + 2 * lane;
+        const float* ap = A + (int64_t)rb * np + c0;
+        float2 a[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(ap + (int64_t)k * np));
+        const float rj0 = TRD_RAW(c0), rj1 = TRD_RAW(c0 + 1);
+        const int ri_r = rb + (lane & 15);
+        const float ri = TRD_RAW(ri_r);
+        const float vj0 = TRD_VFIX(c0, rj0), vj1 = TRD_VFIX(c0 + 1, rj1);
+        const float vi_l = TRD_VFIX(ri_r, ri);
+        float rs[16];
+        float c0acc = 0.f, c1acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float vi = __shfl_sync(0xffffffffu, vi_l, k);
+          rs[k] = fmaf(a[k].x, vj0, a[k].y * vj1);
+          c0acc = fmaf(a[k].x, vi, c0acc);
+          c1acc = fmaf(a[k].y, vi, c1acc);
+        }
+        const float tot = reduce16(rs, lane);
+        const int rid = (lane >> 1) & 15;
+        const float vi_r = __shfl_sync(0xffffffffu, vi_l, rid);
+        if ((lane & 1) == 0) {
+          mt.part[(int64_t)J * np + rb + rid] = tot;
+          const float t = tot * vi_r;
+          vav += (I == J) ? t : 2.f * t;
+        }
+        if (I != J) {
+          sub_sync8(sg8);                            // previous tile's readers are done with cs
+          cs[sw4 * T + 2 * lane] = c0acc;
+          cs[sw4 * T + 2 * lane + 1] = c1acc;
+          sub_sync8(sg8);
+          if (st_tid < T) {
+            const float t = (cs[st_tid] + cs[T + st_tid]) + (cs[2 * T + st_tid] + cs[3 * T + st_tid]);
+            mt.part[(int64_t)I * np + J * T + st_tid] = t;
+          }
+        }
+      }
+    }
+    TRD_STAMP(1);      // VT write + tile products
+    // per-CTA partials of p1 = W^T v, p2 = V^T v: warp w takes row 32 k + w of every owned block (lane = panel column)
+    float p1 = 0.f, p2 = 0.f;
+    if (P > 0) {
+      for (int kp = kfirst; kp < nrb; kp += BP * ncta) {
+        float raw[BP], wv[BP], vv[BP];
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {               // loads of up to BP blocks first ...
+          const int k = kp + q * ncta, r = k * 32 + warp;
+          raw[q] = 0.f; wv[q] = 0.f; vv[q] = 0.f;
+          if (k < nrb && r >= s1 && r < n) {         // warp-uniform
+            raw[q] = TRD_RAW(r);
+            if (lane < P) { wv[q] = __ldcg(mt.Wp + r * NB + lane); vv[q] = __ldcg(mt.Vp + r * NB + lane); }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {               // ... then their use
+          const float v = TRD_VFIX((kp + q * ncta) * 32 + warp, raw[q]);
+          p1 = fmaf(wv[q], v, p1);
+          p2 = fmaf(vv[q], v, p2);
+        }
+      }
+    }
+    vav = warp_sum(vav);
+    red[warp * 66 + lane] = p1;
+    red[warp * 66 + 32 + lane] = p2;
+    if (lane == 0) red[warp * 66 + 64] = vav;
+    __syncthreads();
+    if (tid < 65) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int w = 0; w < 32; ++w) t += red[w * 66 + tid];
+      slot_store(&slots[tid * ncta + cta], (unsigned)(s + 1), t);   // release: the tile partials of this CTA are visible first
+    }
+    TRD_STAMP(2);      // dots + CTA reduction
+    // =========================================================== phase B
+    {
+      // ---- every global load of the phase is issued before any of them is used (they are mutually independent);
+      // blocks / tile classes without work are skipped by uniform branches
+      float* Gs = stage;                               // [BP][32 warps][33]
+      float g[BP], vr[BP], wr[BP], ac[BP], rw[BP];
+      int kpass = kfirst;
+      // own rows (written by this CTA or before the last barrier): may be loaded before the barrier completes
+      auto load_rows = [&](int kp) {
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = kp + q * ncta;
+          vr[q] = 0.f; wr[q] = 0.f; ac[q] = 0.f; rw[q] = 0.f;
+          const int r = k * 32 + warp;                 // finish: warp = row, lane = panel column
+          if (k < nrb && r >= s1 && r < n) {           // uniform
+            if (lane < P) { vr[q] = __ldcg(mt.Vp + r * NB + lane); wr[q] = __ldcg(mt.Wp + r * NB + lane); }
+            if (r > s1) ac[q] = __ldcg(A + (int64_t)r * np + s1);
+            rw[q] = TRD_RAW(r);
+          }
+        }
+      };
+      // tile partials of the other CTAs: only after the barrier
+      auto load_gather = [&](int kp) {
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = kp + q * ncta;
+          g[q] = 0.f;
+          const int rl = k * 32 + lane;                // gather: lane = row, warp = tile class
+          if (k < nrb && rl < n) {
+            const float* pp = mt.part + (int64_t)(b0 + warp) * np + rl;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            if (b0 + warp < nblk) g0 = __ldcg(pp);
+            if (b0 + warp + 32 < nblk) g1 = __ldcg(pp + (int64_t)32 * np);
+            if (b0 + warp + 64 < nblk) g2 = __ldcg(pp + (int64_t)64 * np);
+            g[q] = (g0 + g1) + g2;
+          }
+        }
+      };
+      load_rows(kpass);
+      // cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
+      {
+        // polling the flagged partials of p1, p2, vAv is the group barrier after the tile products
+        float sa = 0.f, sb = 0.f, scv = 0.f;
+        if (warp < P) { sa = slot_sum(slots, warp, ncta, (unsigned)(s + 1), lane); sb = slot_sum(slots, 32 + warp, ncta, (unsigned)(s + 1), lane); }
+        if (warp == 0) scv = slot_sum(slots, 64, ncta, (unsigned)(s + 1), lane);
+        if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
+        __syncthreads();                               // every CTA has finished its tile products: the barrier is passed
+        TRD_STAMP(3);  // barrier 1 (= arrival of the flagged partial scalars)
+        load_gather(kpass);
+        // row s+1 (warp 1): y, w and the panel rows V[s+1][:], W[s+1][:]
+        float y1p = 0.f, vrow = 0.f, wrow = 0.f, a11 = 0.f;
+        if (warp == 1) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; if (X < nblk) y1p += __ldcg(&mt.part[(int64_t)X * np + s1]); }
+          if (lane < P) { vrow = __ldcg(mt.Vp + s1 * NB + lane); wrow = __ldcg(mt.Wp + s1 * NB + lane); }
+          a11 = __ldcg(&A[(int64_t)s1 * np + s1]);
+        }
+        if (warp == 1) {
+          const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
+          const float ytv1 = sc[64] - 2.f * warp_sum(p1l * p2l);
+          const float y1 = warp_sum(y1p - (vrow * p1l + wrow * p2l));
+          const float w1v = tau * (y1 - 0.5f * tau * ytv1);          // v[s+1] = 1
+          if (lane == P) { vrow = 1.f; wrow = w1v; }
+          s_vrow[lane] = vrow; s_wrow[lane] = wrow;
+          const float dd = warp_sum(vrow * wrow);
+          if (lane == 0) { sc[68] = ytv1; sc[69] = w1v; if (cta == 0) mt.d[s1] = a11 - 2.f * dd; }
+        }
+      }
+      TRD_STAMP(4);    // phase B loads, cross-CTA sums, row s+1
+      // the gathered partial sums go through shared memory: (warp = tile class, lane = row) -> (lane = class, warp = row)
+#pragma unroll
+      for (int q = 0; q < BP; ++q) if (kpass + q * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
+      __syncthreads();
+      TRD_STAMP(5);    // gather through shared memory
+      const float ytv = sc[68], w1 = sc[69];
+      const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
+      const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
+      float sig = 0.f;
+      for (; kpass < nrb; kpass += BP * ncta) {
+        // warp w finishes row 32 k + w of each block of the pass (lane = panel column): y, w, x' and its norm partial
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const int k = kpass + q * ncta, r = k * 32 + warp;
+          if (k >= nrb || r < s1 || r >= n) continue;             // warp-uniform
+          const float v = TRD_VFIX(r, rw[q]);
+          const float y = warp_sum(Gs[(q * 32 + lane) * 33 + warp] - (vr[q] * p1l + wr[q] * p2l));
+          const float xs = warp_sum(vr[q] * wsl + wr[q] * vsl);
+          if (lane == 0) {
+            const float w = tau * (y - 0.5f * tau * ytv * v);
+            mt.Wp[r * NB + P] = w;
+            mt.Vp[r * NB + P] = v;
+            if (r > s1) {
+              const float x = ac[q] - xs - (v * w1 + w);          // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
+              col[r] = x;
+              if (r > s1 + 1) sig = fmaf(x, x, sig);
+            }
+          }
+        }
+        if (kpass + BP * ncta < nrb) {                   // another pass (small groups only): reload, regather
+          __syncthreads();
+          load_rows(kpass + BP * ncta);
+          load_gather(kpass + BP * ncta);
+#pragma unroll
+          for (int q = 0; q < BP; ++q) if (kpass + (BP + q) * ncta < nrb) Gs[(q * 32 + warp) * 33 + lane] = g[q];
+          __syncthreads();
+        }
+      }
+      sig = warp_sum(sig);
+      if (lane == 0) red[warp] = sig;
+      __syncthreads();
+      if (warp == 0) {
+        const float t = warp_sum(red[lane]);
+        if (lane == 0) slot_store(&slots[65 * ncta + cta], (unsigned)(s + 2), t);   // release: col / panel column first
+      }
+      P += 1;
+    }
+    TRD_STAMP(6);      // finish rows + norm partial
+#undef TRD_RAW
+#undef TRD_VFIX
   }
   if (cta == 0 && tid == 0) { mt.e[n - 1] = 0.f; mt.tau[n - 1] = 0.f; }
 }
@@ -535,6 +568,15 @@ int launch_sytrd(const TrdMat* d_mats, const TrdJob* d_jobs, int njobs, int np_m
   // cooperative launch: every CTA of the grid is resident (the group barriers spin)
   KFAC_CUDA(cudaLaunchCooperativeKernel((const void*)sytrd_kernel, dim3(grid), dim3(TRD_THREADS), args, smem, s));
   count_launch(1);
+  return KFAC_OK;
+}
+
+// test hook: switch the phase timers on / read them (cycles summed over the CTA 0 of every group)
+int sytrd_profile(int on, unsigned long long* out16) {
+  if (out16) KFAC_CUDA(cudaMemcpyFromSymbol(out16, g_trd_prof, sizeof(unsigned long long) * 16));
+  unsigned long long zero[16] = {0};
+  KFAC_CUDA(cudaMemcpyToSymbol(g_trd_prof, zero, sizeof(zero)));
+  KFAC_CUDA(cudaMemcpyToSymbol(g_trd_prof_on, &on, sizeof(int)));
   return KFAC_OK;
 }
 
