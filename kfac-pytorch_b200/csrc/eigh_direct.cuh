@@ -15,8 +15,7 @@ constexpr int TRD_NB = 32;        // panel width (columns per block reflector of
 constexpr int TRD_T = 64;         // tile edge of the lower-triangle tiling
 constexpr int TRD_THREADS = 1024; // 4 sub-groups of 8 warps
 constexpr int TRD_BT = 128;       // Householder vectors per block reflector of the back-transformation
-constexpr int TRD_CP = 144;       // 4-byte words per CTA of the flagged partial scalars: 66 slots of (epoch, value):
-                                  // [0,32) W^T v, [32,64) V^T v, 64 v^T A v, 65 |x|^2   (zeroed before launch)
+constexpr int TRD_CP = 72;        // floats of per-CTA partial scalars: [0,32) W^T v, [32,64) V^T v, 64 v^T A v, 65 |x|^2
 
 struct TrdMat {
   float* A;        // np x np working copy of F (zero padded); only tiles I >= J are kept up to date
@@ -29,7 +28,7 @@ struct TrdMat {
   float* Wp;       // np x TRD_NB panel of w vectors
   float* part;     // nblk x np partial products of the symmetric matrix-vector product
   float* col;      // np  effective next column
-  float* cpart;    // 66 x ncta slots of (epoch << 32 | float bits), transposed [scalar][cta]: the partial scalars ARE the barrier
+  float* cpart;    // 66 x ncta per-CTA partial scalars, transposed [scalar][cta]
   unsigned int* bar;  // group barrier counter (zeroed before launch)
   int n, np, nblk, ldv;
 };

@@ -31,37 +31,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 
-// flagged 64-bit slots (epoch << 32 | float bits): data and arrival flag in one word
-__device__ __forceinline__ void slot_store(unsigned long long* p, unsigned epoch, float v) {
-  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long slot_load(const unsigned long long* p) {
-  unsigned long long w;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-  return w;
-}
-// sum over the CTAs of slot row `row` once every CTA has published epoch `epoch` (whole warp; lanes take ctas lane, lane+32, ..)
-__device__ __forceinline__ float slot_sum(const unsigned long long* slots, int row, int ncta, unsigned epoch, int lane) {
-  const unsigned long long* p = slots + (size_t)row * ncta;
-  unsigned long long w[5];
-  for (;;) {
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {                  // groups have at most 160 CTAs
-      const int c = lane + 32 * j;
-      w[j] = c < ncta ? slot_load(p + c) : ((unsigned long long)epoch << 32);
-      ok = ok && ((unsigned)(w[j] >> 32) == epoch);
-    }
-    if (ok) break;
-  }
-  float acc = ((__uint_as_float((unsigned)w[0]) + __uint_as_float((unsigned)w[1])) +
-               (__uint_as_float((unsigned)w[2]) + __uint_as_float((unsigned)w[3]))) + __uint_as_float((unsigned)w[4]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  return acc;
-}
-
 __device__ __forceinline__ void group_barrier(unsigned* bar, unsigned& epoch, int ncta) {
   __syncthreads();
   if (ncta > 1) {
@@ -167,7 +136,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
   __shared__ int s_ntile[12];
   unsigned epoch = 0;
   float* const col = mt.col;
-  unsigned long long* const slots = reinterpret_cast<unsigned long long*>(mt.cpart);
+  float* const cpart = mt.cpart;
   const float* __restrict__ A = mt.A;
 
   if (n == 1) {
@@ -209,9 +178,10 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     __syncthreads();
     if (warp == 0) {
       const float t = warp_sum(red[lane]);
-      if (lane == 0) { slot_store(&slots[65 * ncta + cta], 1u, t); if (cta == 0) mt.d[0] = __ldcg(&A[0]); }
+      if (lane == 0) { cpart[65 * ncta + cta] = t; if (cta == 0) mt.d[0] = __ldcg(&A[0]); }
     }
   }
+  group_barrier(mt.bar, epoch, ncta);
 
   int P = 0;                                         // columns in the current panel
   const bool prof = g_trd_prof_on != 0 && cta == 0;
@@ -230,11 +200,12 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
     const int b0 = s1 / T, rb_first = s1 / 32;
     while (kfirst < rb_first) kfirst += ncta;
     // =========================================================== phase C: Householder scalars (warp 0)
-    // (the |x|^2 partials carry the arrival flags of the previous phase: polling them IS the group barrier; `col`
-    // and the panel columns written before the partials are visible once all of them have arrived)
     if (warp == 0) {
-      const float sigma = slot_sum(slots, 65, ncta, (unsigned)(s + 1), lane);
+      float sgp[NCP];
+#pragma unroll
+      for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; sgp[j] = c < ncta ? __ldcg(&cpart[65 * ncta + c]) : 0.f; }
       const float alpha = __ldcg(&col[s1]);
+      const float sigma = warp_sum(sum5(sgp));
       if (lane == 0) {
         float beta, tau, scal;
         if (sigma == 0.f) { beta = alpha; tau = 0.f; scal = 0.f; }
@@ -401,9 +372,11 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       float t = 0.f;
 #pragma unroll 8
       for (int w = 0; w < 32; ++w) t += red[w * 66 + tid];
-      slot_store(&slots[tid * ncta + cta], (unsigned)(s + 1), t);   // release: the tile partials of this CTA are visible first
+      cpart[tid * ncta + cta] = t;
     }
     TRD_STAMP(2);      // dots + CTA reduction
+    group_barrier(mt.bar, epoch, ncta);
+    TRD_STAMP(3);      // barrier 1
     // =========================================================== phase B
     {
       // ---- every global load of the phase is issued before any of them is used (they are mutually independent);
@@ -443,17 +416,27 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         }
       };
       load_rows(kpass);
+      load_gather(kpass);
       // cross-CTA sums of p1, p2, vAv: warp w owns outputs w (p1), 32 + w (p2) and (warp 0) 64
       {
-        // polling the flagged partials of p1, p2, vAv is the group barrier after the tile products
         float sa = 0.f, sb = 0.f, scv = 0.f;
-        if (warp < P) { sa = slot_sum(slots, warp, ncta, (unsigned)(s + 1), lane); sb = slot_sum(slots, 32 + warp, ncta, (unsigned)(s + 1), lane); }
-        if (warp == 0) scv = slot_sum(slots, 64, ncta, (unsigned)(s + 1), lane);
-        if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
-        __syncthreads();                               // every CTA has finished its tile products: the barrier is passed
-        TRD_STAMP(3);  // barrier 1 (= arrival of the flagged partial scalars)
-        load_gather(kpass);
-        // row s+1 (warp 1): y, w and the panel rows V[s+1][:], W[s+1][:]
+        if (warp < P) {
+          float ca[NCP], cb[NCP];
+#pragma unroll
+          for (int j = 0; j < NCP; ++j) {
+            const int c = lane + 32 * j;
+            ca[j] = c < ncta ? __ldcg(&cpart[warp * ncta + c]) : 0.f;
+            cb[j] = c < ncta ? __ldcg(&cpart[(32 + warp) * ncta + c]) : 0.f;
+          }
+          sa = sum5(ca); sb = sum5(cb);
+        }
+        if (warp == 0) {
+          float cc[NCP];
+#pragma unroll
+          for (int j = 0; j < NCP; ++j) { const int c = lane + 32 * j; cc[j] = c < ncta ? __ldcg(&cpart[64 * ncta + c]) : 0.f; }
+          scv = sum5(cc);
+        }
+        // row s+1 (warp 1): raw loads now, the rest after the sums are published
         float y1p = 0.f, vrow = 0.f, wrow = 0.f, a11 = 0.f;
         if (warp == 1) {
 #pragma unroll
@@ -461,6 +444,10 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
           if (lane < P) { vrow = __ldcg(mt.Vp + s1 * NB + lane); wrow = __ldcg(mt.Wp + s1 * NB + lane); }
           a11 = __ldcg(&A[(int64_t)s1 * np + s1]);
         }
+        if (warp < P) { sa = warp_sum(sa); sb = warp_sum(sb); }
+        if (warp == 0) scv = warp_sum(scv);
+        if (lane == 0) { sc[warp] = sa; sc[32 + warp] = sb; if (warp == 0) sc[64] = scv; }
+        __syncthreads();
         if (warp == 1) {
           const float p1l = (lane < P) ? sc[lane] : 0.f, p2l = (lane < P) ? sc[32 + lane] : 0.f;
           const float ytv1 = sc[64] - 2.f * warp_sum(p1l * p2l);
@@ -516,11 +503,13 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       __syncthreads();
       if (warp == 0) {
         const float t = warp_sum(red[lane]);
-        if (lane == 0) slot_store(&slots[65 * ncta + cta], (unsigned)(s + 2), t);   // release: col / panel column first
+        if (lane == 0) cpart[65 * ncta + cta] = t;
       }
       P += 1;
     }
     TRD_STAMP(6);      // finish rows + norm partial
+    group_barrier(mt.bar, epoch, ncta);
+    TRD_STAMP(7);      // barrier 2
 #undef TRD_RAW
 #undef TRD_VFIX
   }
