@@ -101,8 +101,12 @@ int kfac_factor_ema(const kfac_ema_item* items, int count, float alpha,
  * KFACEigenLayer.compute_{a,g}_inv (kfac/layers/eigen.py:295-344).
  * F (n x n, symmetric PSD) -> Q (n x n row-major, COLUMNS are eigenvectors,
  * same convention as torch.linalg.eigh) and d (n eigenvalues >= 0, in the
- * order of Q's columns -- NOT sorted).  All matrices of the batch are solved
- * concurrently (block one-sided Jacobi; n <= 128 solved in shared memory). */
+ * order of Q's columns: ascending for n > 128, unsorted for n <= 128).
+ * All matrices of the batch are solved concurrently:
+ *   n <= 128  two-sided Jacobi, the whole matrix in the shared memory of one CTA;
+ *   n  > 128  Householder tridiagonalisation (one persistent kernel for the batch, CTA groups per
+ *             matrix) -> divide and conquer on the tridiagonal matrix -> block-reflector
+ *             back-transformation (grouped tcgen05 GEMMs) -- the stages of LAPACK's ssyevd. */
 typedef struct kfac_eigh_item {
   const float* F; /* n x n dense (ld = n) */
   float* Q;       /* n x n, leading dimension ldq */
@@ -110,13 +114,18 @@ typedef struct kfac_eigh_item {
   float* d;
   int n;
   int ldq;        /* 0 -> n.  Multiples of 4 let the tensor-core GEMMs consume Q directly */
-  const float* V0T; /* optional warm start (n > 128): TRANSPOSE of an orthonormal starting basis,
-                       ld = ldq -- typically the QT of the previous call (may alias QT); NULL = identity */
+  const float* V0T; /* ignored (warm start of the round-1 iterative solver; kept for ABI compatibility) */
 } kfac_eigh_item;
 size_t kfac_eigh_workspace_bytes(const int* n, int count);
-/* max_sweeps <= 0 -> default (40); tol <= 0 -> automatic (pairs above 3e-6 are rotated; done when a sweep starts below 2e-5 or its RMS contamination is below 3e-5) */
+/* max_sweeps <= 0 -> default (24 sweeps of the n <= 128 Jacobi); tol is ignored.
+ * The first int of the workspace is a device status word written by the call (0 = fine, bit 0 = an
+ * iteration did not converge, bit 1 = a non-finite eigenvalue): fetch it with kfac_eigh_status(). */
 int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* ws,
                       size_t ws_bytes, int max_sweeps, float tol, void* stream);
+/* asynchronous copy of the status word of the last kfac_eigh_batched() on this workspace into
+ * (pinned) host memory; valid once `stream` has passed this point.  torch.linalg.eigh raises in
+ * these cases (eigen.py:310); the caller maps a non-zero word to KFAC_ERR_NO_CONVERGE. */
+int kfac_eigh_status(const void* ws, int* host_status, void* stream);
 
 /* K6: replaces eigen.py:345-348: out[i,j] = 1 / (dg[i]*da[j] + damping) */
 int kfac_dgda(const float* dg, const float* da, int g, int a, float damping,

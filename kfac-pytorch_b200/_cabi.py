@@ -62,6 +62,7 @@ SIGNATURES = {
     'kfac_factor_ema': (c_int, [C.POINTER(EmaItem), c_int, c_float, c_void_p]),
     'kfac_eigh_workspace_bytes': (c_size_t, [C.POINTER(c_int), c_int]),
     'kfac_eigh_batched': (c_int, [C.POINTER(EighItem), c_int, c_void_p, c_size_t, c_int, c_float, c_void_p]),
+    'kfac_eigh_status': (c_int, [c_void_p, c_void_p, c_void_p]),
     'kfac_dgda': (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     'kfac_inverse_from_eigh': (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'kfac_transpose': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),

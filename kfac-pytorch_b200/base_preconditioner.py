@@ -211,12 +211,9 @@ class BaseKFACPreconditioner:
         self._factors_dirty = False
         self._pending_alpha: dict[float, list[tuple[KFACLayer, str]]] = {}
         self.last_grad_scale: torch.Tensor | None = None   # device scalar nu of the last step
-        # Jacobi warm start: successive factors differ by one EMA step, so the previous
-        # eigenbasis nearly diagonalises the new factor (fewer sweeps, same result)
-        self.warm_start = True
         # store preconditioned gradients straight into the receivers' arenas (P2P) instead of broadcasting
         self.fused_grad_broadcast = True
-        self._have_basis: set[int] = set()
+        self._eig_status: torch.Tensor | None = None     # pinned host int: status word of the last eigensolver call
 
         for module in self._layers:
             module.register_forward_pre_hook(self._save_input)
@@ -542,6 +539,7 @@ class BaseKFACPreconditioner:
         `loss.backward()` and `optimizer.step()`; gradients must already be
         averaged across ranks (base_preconditioner.py:310-382)."""
         self._ensure_arenas()
+        self._check_eigh_status(wait=False)
         if not self._update_factors_in_hook and self.steps % self.factor_update_steps == 0:
             for name, layer in reversed(self._layer_list()):
                 self._mini_steps[name] = 0
@@ -591,6 +589,21 @@ class BaseKFACPreconditioner:
             return
         self._tdc.allreduce_average(self._factor_arena, group=None)
 
+    def _check_eigh_status(self, wait: bool) -> None:
+        """Raise if the last eigendecomposition reported non-convergence or non-finite eigenvalues
+        (KFAC_ERR_NO_CONVERGE).  wait=False: only if the status word has already arrived."""
+        if not getattr(self, '_eig_pending', False):
+            return
+        if not wait and not self._eig_event.query():
+            return
+        self._eig_event.synchronize()
+        self._eig_pending = False
+        word = int(self._eig_status.item())
+        if word:
+            why = ' and '.join(w for b, w in ((1, 'an iteration did not converge'), (2, 'non-finite eigenvalues')) if word & b)
+            raise _cabi.KFACNativeError(f'eigendecomposition of the K-FAC factors failed: {why} '
+                                        f'(status {_cabi.KFAC_ERR_NO_CONVERGE}); were the factors finite?')
+
     # K5/K6/K7 + C2 -------------------------------------------------------
     def _compute_inverses(self) -> None:
         self._ensure_arenas()
@@ -632,17 +645,22 @@ class BaseKFACPreconditioner:
             items = (_cabi.EighItem * len(eig))()
             ns = (C.c_int * len(eig))()
             for i, (F, Q, QT, d, n) in enumerate(eig):
-                # warm start from the previous eigenbasis of this factor when there is one
-                warm = QT.data_ptr() if (QT is not None and self.warm_start and id(QT) in self._have_basis) else None
                 items[i] = _cabi.EighItem(F.data_ptr(), Q.data_ptr(), QT.data_ptr() if QT is not None else None,
-                                          d.data_ptr(), n, _cabi.ld4(n), warm)
-                if QT is not None:
-                    self._have_basis.add(id(QT))
+                                          d.data_ptr(), n, _cabi.ld4(n), None)
                 ns[i] = n
             need = lib.kfac_eigh_workspace_bytes(ns, len(eig))
             ws = self._eig_scratch.get(need, self._device)
             _cabi.check(lib.kfac_eigh_batched(items, len(eig), ws.data_ptr(), need, 0, 0.0, stream),
                         'kfac_eigh_batched')
+            # status word (non-convergence / non-finite eigenvalues): copied to pinned memory without a sync and
+            # inspected before the NEXT use of the second-order data (torch.linalg.eigh raises immediately,
+            # kfac/layers/eigen.py:310; here the error surfaces one call later instead of stalling the stream)
+            if self._eig_status is None:
+                self._eig_status = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._eig_event = torch.cuda.Event()
+            _cabi.check(lib.kfac_eigh_status(ws.data_ptr(), self._eig_status.data_ptr(), stream), 'kfac_eigh_status')
+            self._eig_event.record()
+            self._eig_pending = True
         for layer, what in post:
             I = layer._inv
             if what == 'dgda':

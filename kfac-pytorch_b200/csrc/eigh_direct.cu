@@ -74,9 +74,13 @@ __global__ void copy_rows_kernel(const float* src, int lds, float* dst, int ldd,
     dst[(int64_t)i * ldd + j] = src[(int64_t)i * lds + j];
   }
 }
-__global__ void clamp_copy_kernel(const float* src, float* dst, int n) {
+__global__ void clamp_copy_kernel(const float* src, float* dst, int n, int* status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = fmaxf(src[i], 0.f);
+  if (i < n) {
+    const float v = src[i];
+    if (!isfinite(v) && status) atomicOr(status, 2);
+    dst[i] = fmaxf(v, 0.f);
+  }
 }
 
 struct MatLayout {
@@ -226,7 +230,7 @@ size_t eigh_direct_workspace_bytes(const int* n, int count) {
 
 // stage selector for tests / profiling: 1 = stop after the tridiagonalisation (d, e in the items' d / Q row 0),
 // 0 = full solve
-int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, cudaStream_t s) {
+int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, int* status, cudaStream_t s) {
   if (count <= 0) return KFAC_OK;
   std::vector<int> ns(count);
   for (int i = 0; i < count; ++i) ns[i] = items[i].n;
@@ -272,7 +276,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
   KFAC_CUDA(cudaMemcpyAsync(d_dc, dc.data(), sizeof(DcMat) * count, cudaMemcpyHostToDevice, s));
   int rc;
   if ((rc = launch_sytrd(d_trd, d_jobs, (int)jobs.size(), np_max, G, s))) return rc;
-  if ((rc = launch_stedc(dc.data(), d_dc, count, base + L.off_plan, L.plan_bytes, s))) return rc;
+  if ((rc = launch_stedc(dc.data(), d_dc, count, base + L.off_plan, L.plan_bytes, status, s))) return rc;
 
   // ---- back-transformation: QT = Z^T B_{L-1}^T ... B_0^T, B_k = I - V_k T_k V_k^T
   std::vector<BtBlock> blocks;
@@ -368,7 +372,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     }
     transpose_ld_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32)), dim3(32, 8), 0, s>>>(ZT, np, items[i].Q, ldq, n, n);
     KFAC_LAUNCH_CHECK();
-    clamp_copy_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d.d, items[i].d, n);
+    clamp_copy_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d.d, items[i].d, n, status);
     KFAC_LAUNCH_CHECK();
   }
   return KFAC_OK;
@@ -440,7 +444,7 @@ extern "C" int kfac_experimental_stedc(const float* d_in, const float* e_in, int
   if (n > 1) KFAC_CUDA(cudaMemcpyAsync(m.e, e_in, (size_t)(n - 1) * 4, cudaMemcpyDeviceToDevice, s));
   KFAC_CUDA(cudaMemcpyAsync(base + oMat, &m, sizeof(m), cudaMemcpyHostToDevice, s));
   int rc;
-  if ((rc = launch_stedc(&m, (DcMat*)(base + oMat), 1, base + oPlan, pb, s))) return rc;
+  if ((rc = launch_stedc(&m, (DcMat*)(base + oMat), 1, base + oPlan, pb, nullptr, s))) return rc;
   KFAC_CUDA(cudaMemcpyAsync(evals, m.d, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
   KFAC_CUDA(cudaMemcpy2DAsync(Q, (size_t)n * 4, m.Q[m.result_buf], (size_t)np * 4, (size_t)n * 4, n, cudaMemcpyDeviceToDevice, s));
   return KFAC_OK;

@@ -57,11 +57,8 @@ struct DcPlanHost;   // opaque (stedc.cu)
 size_t stedc_plan_bytes(const int* n, int count);   // includes the grouped-GEMM tables
 // eigen-decomposition of `count` tridiagonal matrices; d_mats/h_mats describe them (device pointers inside);
 // plan_ws: device scratch of stedc_plan_bytes(); all work is enqueued on `s`
-int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, cudaStream_t s);
-
-// leaf solver exported by eigh.cu (shared-memory Jacobi on dense <= 64 x 64 problems, direct mode)
-struct EighMat;
-int launch_jacobi_direct64(EighMat* d_mats, const int* d_list, int count, cudaStream_t s);
+// status: device int, bit 0 is set when a leaf QL iteration did not converge
+int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, int* status, cudaStream_t s);
 
 // plain fp32 TN GEMM on the tcgen05 engine: D = alpha * A B^T (+ D when accumulate)
 int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
@@ -79,7 +76,8 @@ struct StreamPool {
 StreamPool& stream_pool();
 
 size_t eigh_direct_workspace_bytes(const int* n, int count);
-int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, cudaStream_t s);
+// status: device int (bit 0: an iteration did not converge, bit 1: non-finite eigenvalue); may be nullptr
+int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, int* status, cudaStream_t s);
 int gemm_tn_acc(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,
                 int K, float alpha, cudaStream_t s);
 

@@ -60,7 +60,7 @@ __global__ void dc_cut_kernel(const DcMat* mats, const DcCut* cuts, int ncuts) {
 }
 
 // ------------------------------------------------------------------ leaves: implicit QL, one warp per leaf
-__global__ void __launch_bounds__(64) dc_leaf_kernel(const DcMat* mats, const DcLeaf* leaves, int nleaves) {
+__global__ void __launch_bounds__(64) dc_leaf_kernel(const DcMat* mats, const DcLeaf* leaves, int nleaves, int* status) {
   __shared__ float Z[2][LEAF][LEAF + 1];     // Z[w][col][row]
   __shared__ float sd[2][LEAF], se[2][LEAF];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(64) dc_leaf_kernel(const DcMat* mats, const Dc
   __syncwarp();
   // every lane runs the same scalar recurrence; lane l rotates rows l, l + 32 of the eigenvector matrix
   for (int l = 0; l < n; ++l) {
-    for (int iter = 0; iter < 60; ++iter) {
+    for (int iter = 0; ; ++iter) {
+      if (iter == 60) { if (lane == 0 && status) atomicOr(status, 1); break; }   // no convergence (LAPACK: info > 0)
       int m = l;
       for (; m < n - 1; ++m) {
         const float dd = fabsf(d[m]) + fabsf(d[m + 1]);
@@ -460,7 +461,7 @@ size_t stedc_plan_bytes(const int* n, int count) {
          align_up(sizeof(DcMerge) * merges + 256 * (pl.levels.size() + 1), 256) + align_up(grouped_gemm_ws_bytes((int)widest), 256);
 }
 
-int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, cudaStream_t s) {
+int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, int* status, cudaStream_t s) {
   std::vector<int> ns(count);
   for (int i = 0; i < count; ++i) ns[i] = h_mats[i].n;
   Plan pl;
@@ -493,7 +494,7 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
     dc_cut_kernel<<<ceil_div(pl.cuts.size(), 256), 256, 0, s>>>(d_mats, d_cuts, (int)pl.cuts.size());
     KFAC_LAUNCH_CHECK();
   }
-  dc_leaf_kernel<<<ceil_div(pl.leaves.size(), 2), 64, 0, s>>>(d_mats, d_leaves, (int)pl.leaves.size());
+  dc_leaf_kernel<<<ceil_div(pl.leaves.size(), 2), 64, 0, s>>>(d_mats, d_leaves, (int)pl.leaves.size(), status);
   KFAC_LAUNCH_CHECK();
   static bool attr = false;
   if (!attr) {

@@ -95,28 +95,6 @@ __device__ __forceinline__ float reduce16(float (&r)[16], int lane) {
   return r[0];
 }
 
-// sums of 8 per-lane values over the warp with 9 shuffles: afterwards every lane holds the complete sum
-// of value number rowid(lane) = bit2 | bit3 << 1 | bit4 << 2 of its lane index
-__device__ __forceinline__ float reduce8(float (&r)[8], int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float keep = (lane & 16) ? r[i + 4] : r[i], send = (lane & 16) ? r[i] : r[i + 4];
-    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float keep = (lane & 8) ? r[i + 2] : r[i], send = (lane & 8) ? r[i] : r[i + 2];
-    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  {
-    const float keep = (lane & 4) ? r[1] : r[0], send = (lane & 4) ? r[0] : r[1];
-    r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 2);
-  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-  return r[0];
-}
-
 // One column costs two dependent L2 round trips and two group barriers: every phase first ISSUES all its global
 // loads (they are mutually independent), then computes.  cpart is stored transposed ([scalar][cta]) so that the
 // cross-CTA reductions read contiguous lines.

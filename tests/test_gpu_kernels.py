@@ -241,19 +241,26 @@ def test_eigh_large(lib, dev):
         check_eigh(F, Q, d)
 
 
-def test_eigh_wide_pairs_variant():
-    # KFAC_EIGH_WIDE=1 (64-column blocks, 128x128 pair problems) is read once per process:
-    # run the tensor-core-class eigensolver tests again in a child with the switch on
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, KFAC_EIGH_WIDE='1')
-    here = os.path.abspath(__file__)
-    out = subprocess.run([sys.executable, '-m', 'pytest', here, '-q', '-m', 'gpu', '-x', '-k',
-                          'eigh_tc_class or eigh_large', '-p', 'no:cacheprovider'],
-                         env=env, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert '2 passed' in out.stdout, out.stdout[-500:]
+def test_eigh_reports_non_finite_input(lib, dev):
+    """A factor with an Inf (AMP overflow step) must not yield a silently wrong eigenbasis: the status word of
+    the workspace reports it (torch.linalg.eigh raises in the reference, kfac/layers/eigen.py:310)."""
+    from kfac_b200 import _cabi
+    for n in (40, 300):
+        F = make_psd(n, 'cov', n).to(dev).contiguous()
+        F[n // 2, n // 3] = float('inf')
+        F[n // 3, n // 2] = float('inf')
+        ld = _cabi.ld4(n)
+        Q = torch.zeros(n, ld, device=dev)
+        d = torch.empty(n, device=dev)
+        items = (_cabi.EighItem * 1)(_cabi.EighItem(F.data_ptr(), Q.data_ptr(), None, d.data_ptr(), n, ld, None))
+        ns = (C.c_int * 1)(n)
+        need = lib.kfac_eigh_workspace_bytes(ns, 1)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        assert lib.kfac_eigh_batched(items, 1, ws.data_ptr(), need, 0, 0.0, S()) == 0
+        host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        assert lib.kfac_eigh_status(ws.data_ptr(), host.data_ptr(), S()) == 0
+        torch.cuda.synchronize()
+        assert int(host.item()) != 0, n
 
 
 def test_dgda_and_inverse(lib, dev):

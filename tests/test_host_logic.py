@@ -208,21 +208,6 @@ def test_arena_entries_are_16_byte_aligned():
     assert _storage_numel((147,)) == 148 and _storage_numel((10, 21)) == 10 * 24
 
 
-def test_systolic_jacobi_host_emulation(tmp_path):
-    """The experimental data-moving Jacobi (csrc/jacobi_systolic.cuh) is plain inline code on explicit
-    worker indices: replay it on the CPU (schedule, crit-thread prediction, convergence)."""
-    import shutil
-    import subprocess
-    if shutil.which('g++') is None:
-        pytest.skip('no g++')
-    exe = tmp_path / 'jsh'
-    src = os.path.join(ROOT, 'tests', 'host', 'jacobi_systolic_host.cpp')
-    inc = os.path.join(ROOT, 'kfac-pytorch_b200', 'csrc')
-    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-std=c++17', '-I', inc, src, '-o', str(exe)], check=True)
-    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and out.stdout.strip().endswith('OK'), out.stdout[-2000:]
-
-
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm) prints ONE JSON
     line with the contract keys; exercised on the small workload so it stays in the CPU budget."""
