@@ -246,7 +246,11 @@ def parity_step(pre, model, world, rank, dev, hp):
                        'oracle_fp32_vs_fp64': float((want - gold).norm() / gold.norm())}
                 if worst_gold is None or e >= worst_gold['b200_vs_oracle_fp32']:
                     worst_gold = rec
-        ok = worst < 1e-3 or (worst_gold is not None and worst_gold['b200_vs_fp64'] <= max(1e-3, worst_gold['oracle_fp32_vs_fp64']))
+        # bar: 1e-3 against the fp32 oracle; a layer on which the fp32 oracle ITSELF is further than that from exact
+        # arithmetic (ill-conditioned factors of the synthetic random-label run) passes when this implementation is
+        # no further from fp64 than 1.5 x the oracle's own distance (both are fp32 roundings of the same operator)
+        ok = worst < 1e-3 or (worst_gold is not None and worst_gold['oracle_fp32_vs_fp64'] > 1e-3 and
+                              worst_gold['b200_vs_fp64'] <= 1.5 * worst_gold['oracle_fp32_vs_fp64'])
         out.update({'worst_layer_P_rel_fro_vs_oracle': worst, 'worst_layer_dims_a_g': worst_layer,
                     'layers_checked': len(layers), 'bar': 1e-3, 'ok': bool(ok),
                     'ill_conditioned_layer_vs_fp64': worst_gold})
@@ -365,6 +369,43 @@ def run_b200(args):
             one_step(False, stationary=True)
         ms_stat, _ = timed_loop(max(3, args.steps // 2), False, stationary=True)
         ms_stat /= max(3, args.steps // 2)
+    # second configuration: the reference's default ImageNet schedule (factor_update_steps 10, inv_update_steps 100,
+    # examples/torch_imagenet_resnet.py:158-198): 20 steps without an eigendecomposition, 2 of them with factor updates
+    sched = None
+    if not args.no_stationary:
+        fu, iu, st = pre._factor_update_steps, pre._inv_update_steps, pre._steps
+        pre._factor_update_steps, pre._inv_update_steps, pre._steps = 10, 100, 1
+        for _ in range(2):
+            one_step(False)
+        pre._steps = 1
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.kfac_launch_count()
+        t_step = []
+        e0.record()
+        for k in range(20):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            opt.zero_grad(set_to_none=True)
+            x, y = devb[k % NB]
+            crit(model(x), y).backward()
+            a.record()
+            pre.step()
+            b.record()
+            opt.step()
+            t_step.append((a, b))
+        e1.record()
+        barrier()
+        ms20 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms20, op=dist.ReduceOp.MAX)
+        plain = sorted(a.elapsed_time(b) for a, b in t_step)
+        sched = {'factor_update_steps': 10, 'inv_update_steps': 100, 'steps': 20, 'ms_per_step': float(ms20.item()) / 20,
+                 'value': B * world * 20 / (float(ms20.item()) / 1e3), 'unit': 'images/s',
+                 'kfac_step_ms_median': plain[len(plain) // 2], 'kfac_step_ms_max': plain[-1],
+                 'gpu_launches_per_step': (lib.kfac_launch_count() - l0) / 20.0,
+                 'note': 'steps 1..20 of the schedule: no eigendecomposition, factor statistics at steps 10 and 20; '
+                         'kfac_step_ms = preconditioner.step() alone (precondition + kl-clip + write-back)'}
+        pre._factor_update_steps, pre._inv_update_steps, pre._steps = fu, iu, st
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(4):
@@ -427,6 +468,7 @@ def run_b200(args):
         # factor hooks that run inside forward/backward
         'kfac_step_ms': sum(v for k, v in phase_ms.items() if k not in ('factor_a', 'factor_g')) / K,
         'kfac_hooks_ms': sum(v for k, v in phase_ms.items() if k in ('factor_a', 'factor_g')) / K,
+        'default_schedule': sched,
         'stationary_input': ({'ms_per_step': ms_stat, 'value': B * world / (ms_stat / 1e3),
                               'note': 'same batch every step (round-1 protocol); not the headline'}
                              if ms_stat else None),

@@ -1,0 +1,5 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 6 --warmup 3 > gpurun_out/r2_19_bench_n2.json 2> gpurun_out/r2_19_bench_n2.err
+echo "exit code $?" >> gpurun_out/r2_19_bench_n2.err
+tail -c 600 gpurun_out/r2_19_bench_n2.err; tail -c 800 gpurun_out/r2_19_bench_n2.json

@@ -384,8 +384,8 @@ def test_triu_pack_unpack(lib, dev, n):
     assert torch.equal(out.cpu(), 0.5 * F)
 
 
-def test_eigh_warm_start(lib, dev):
-    """Second decomposition seeded with the previous eigenbasis (V0T = QT of the first call)."""
+def test_eigh_accepts_v0t(lib, dev):
+    """ABI compatibility: `V0T` (warm start of the round-1 iterative solver, may alias QT) is accepted and ignored."""
     from kfac_b200 import _cabi
     torch.manual_seed(0)
     for n in (200, 576, 1024):
