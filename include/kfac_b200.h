@@ -119,7 +119,7 @@ typedef struct kfac_eigh_item {
 size_t kfac_eigh_workspace_bytes(const int* n, int count);
 /* max_sweeps <= 0 -> default (24 sweeps of the n <= 128 Jacobi); tol is ignored.
  * The first int of the workspace is a device status word written by the call (0 = fine, bit 0 = an
- * iteration did not converge, bit 1 = a non-finite eigenvalue): fetch it with kfac_eigh_status(). */
+ * iteration did not converge, bit 1 = a non-finite (or |x| > 1e15) factor entry, replaced by 0, or a non-finite eigenvalue): fetch it with kfac_eigh_status(). */
 int kfac_eigh_batched(const kfac_eigh_item* items, int count, void* ws,
                       size_t ws_bytes, int max_sweeps, float tol, void* stream);
 /* asynchronous copy of the status word of the last kfac_eigh_batched() on this workspace into

@@ -43,11 +43,15 @@ __global__ void __launch_bounds__(N * 8) jacobi_small_kernel(const SmallMat* mat
   const int tid = threadIdx.x;
   const SmallMat mt = mats[blockIdx.x];
   const int n = mt.n;
+  bool bad_in = false;
   for (int idx = tid; idx < N * N; idx += T) {
     const int i = idx / N, j = idx % N;
-    M[i][j] = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
+    float x = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
+    if (!(fabsf(x) <= 1e15f)) { bad_in = true; x = 0.f; }      // same input rule as the direct solver (eigh_direct.cu)
+    M[i][j] = x;
     W[i][j] = (i == j) ? 1.f : 0.f;
   }
+  if (bad_in) atomicOr(status, 2);
   __syncthreads();
   bool converged = false;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {

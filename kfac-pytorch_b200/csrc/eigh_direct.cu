@@ -43,13 +43,19 @@ __global__ void __launch_bounds__(BT) larft_kernel(const BtBlock* blocks) {
   for (int j = 0; j < BT; ++j) b.Tm[i * BT + j] = Ts[i][j];
 }
 
-// A (np x np, zero padded) <- F (n x n, ld n)
-__global__ void pad_copy_kernel(const float* F, int n, float* A, int np) {
+// A (np x np, zero padded) <- F (n x n, ld n).  Entries that are not finite, or so large that the squared column norms of
+// the reduction could overflow (|x| > 1e15), are replaced by 0 and reported in the status word (bit 1): the solve then
+// runs on finite data (no NaN reaches the index arithmetic of the divide and conquer) and the caller sees the failure.
+__global__ void pad_copy_kernel(const float* F, int n, float* A, int np, int* status) {
   const int64_t total = (int64_t)np * np;
+  bool bad = false;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx / np), j = (int)(idx % np);
-    A[idx] = (i < n && j < n) ? F[(int64_t)i * n + j] : 0.f;
+    float x = (i < n && j < n) ? F[(int64_t)i * n + j] : 0.f;
+    if (!(fabsf(x) <= 1e15f)) { bad = true; x = 0.f; }
+    A[idx] = x;
   }
+  if (bad && status) atomicOr(status, 2);
 }
 
 __global__ void transpose_ld_kernel(const float* src, int lds, float* dst, int ldd, int rows, int cols) {
@@ -131,12 +137,15 @@ void make_layout(const int* n, int count, Layout& L) {
 }
 
 // ---- CTA-group schedule of the tridiagonalisation kernel --------------------------------------
-// model of one matrix on C CTAs: n columns, each t0 (barriers + vector phases) + beta n^2 / C (tile products,
-// averaged over the shrinking trailing matrix)
-// measured on B200 (tests/test_gpu_direct_eigh.py, profiles/): ~10 us of barrier / dependent-load latency per column
-// + 1 ns per row + the tile products
-constexpr double T0 = 8.7e-6, T1 = 4.2e-10, BETA = 1.9e-11;
-double job_time(int n, int C) { return (double)n * (T0 + T1 * n + BETA * (double)n * n / C); }
+// Time model of one matrix on a group of C CTAs, fitted (least squares on the relative error, worst 6 %) to the sweep
+// tests/sytrd_sweep.py over n = 256 .. 4608, C = 1 .. 148 on a B200 (profiles/r02_sytrd_sweep.md): per column
+//   T0 + T1 n            barriers, dependent cross-CTA loads, the serial vector phases
+//   (B n^2 + GA n) / C   tile products of the trailing matrix (averaged over its shrinking size) + row work
+//   DE log2 C            barrier and cross-CTA reduction cost growing with the group
+constexpr double T0 = 7.19e-6, T1 = 2.46e-10, BETA = 1.265e-11, GAMMA = 2.09e-8, DELTA = 2.91e-7, EPS = -1.66e-6;
+double job_time(int n, int C) {
+  return (double)n * (T0 + T1 * n + (BETA * (double)n * n + GAMMA * n + EPS) / C + DELTA * std::log2((double)C));
+}
 
 void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
   // smallest makespan M such that the CTA-time of all jobs (each sized to finish within M) fits into G * M
@@ -144,17 +153,21 @@ void make_schedule(const int* n, int count, int G, std::vector<TrdJob>& jobs) {
     const int nb = (ni + TRD_T - 1) / TRD_T;
     const int cmin = std::min(G, sytrd_min_ctas(ni));
     const int cmax = std::max(cmin, std::min(G, nb * (nb + 1) / 2 / 2 + 1));   // >= 2 tiles per sub-group pays
-    for (int C = cmin; C <= cmax; ++C) if (job_time(ni, C) <= M) return C;
-    return cmax;
+    int fastest = cmin;
+    for (int C = cmin; C <= cmax; ++C) {
+      if (job_time(ni, C) <= M) return C;
+      if (job_time(ni, C) < job_time(ni, fastest)) fastest = C;
+    }
+    return fastest;
   };
   double lo = 0, hi = 0;
-  for (int i = 0; i < count; ++i) { lo = std::max(lo, job_time(n[i], G)); hi += job_time(n[i], 1); }
+  for (int i = 0; i < count; ++i) { lo = std::max(lo, job_time(n[i], ctas_for(n[i], 0.0))); hi += job_time(n[i], std::min(G, sytrd_min_ctas(n[i]))); }
   hi = std::max(hi, lo);
   for (int it = 0; it < 40; ++it) {
     const double M = 0.5 * (lo + hi);
     double area = 0;
     for (int i = 0; i < count; ++i) { const int C = ctas_for(n[i], M); area += C * job_time(n[i], C); }
-    if (area <= 0.9 * G * M) hi = M; else lo = M;
+    if (area <= 0.95 * G * M) hi = M; else lo = M;
   }
   std::vector<int> order(count), C(count);
   for (int i = 0; i < count; ++i) { order[i] = i; C[i] = ctas_for(n[i], hi); }
@@ -257,7 +270,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     d.fscr = (float*)(base + m.fscr); d.iscr = (int*)(base + m.iscr);
     d.n = m.n; d.ld = m.np; d.result_buf = 0;
     // inputs / zeroed state
-    pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)m.np * m.np, 256)), 256, 0, s>>>(items[i].F, m.n, t.A, m.np);
+    pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)m.np * m.np, 256)), 256, 0, s>>>(items[i].F, m.n, t.A, m.np, status);
     KFAC_LAUNCH_CHECK();
     KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)m.np * m.np * 4, s));
     KFAC_CUDA(cudaMemsetAsync(t.Vb, 0, (size_t)m.np * (m.np + BT) * 4, s));
@@ -402,7 +415,7 @@ extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e
   t.e = (float*)(base + oE); t.Vp = (float*)(base + oVp); t.Wp = (float*)(base + oWp); t.part = (float*)(base + oPart);
   t.col = (float*)(base + oCol); t.cpart = (float*)(base + oC); t.bar = (unsigned int*)(base + oBar);
   t.n = n; t.np = np; t.nblk = nblk; t.ldv = np; t.Vb = nullptr;
-  pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)np * np, 256)), 256, 0, s>>>(F, n, t.A, np);
+  pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)np * np, 256)), 256, 0, s>>>(F, n, t.A, np, nullptr);
   KFAC_LAUNCH_CHECK();
   KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)np * np * 4, s));
   KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)np * TRD_NB * 4, s));

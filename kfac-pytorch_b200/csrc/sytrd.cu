@@ -69,6 +69,28 @@ constexpr int NCP = 5;                      // ceil(max CTAs per group / 32)
 
 __device__ __forceinline__ float sum5(const float (&x)[NCP]) { return ((x[0] + x[1]) + (x[2] + x[3])) + x[4]; }
 
+// sums of 8 per-lane values over the warp with 9 shuffles: afterwards every lane holds the complete sum
+// of value number bit2 | bit3 << 1 | bit4 << 2 of its lane index
+__device__ __forceinline__ float reduce8(float (&r)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = (lane & 16) ? r[i + 4] : r[i], send = (lane & 16) ? r[i] : r[i + 4];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = (lane & 8) ? r[i + 2] : r[i], send = (lane & 8) ? r[i] : r[i + 2];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float keep = (lane & 4) ? r[1] : r[0], send = (lane & 4) ? r[0] : r[1];
+    r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 2);
+  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+  return r[0];
+}
+
 // sums of 16 per-lane values over the warp with 16 shuffles: afterwards every lane holds the complete sum of value
 // number (lane >> 1) & 15
 __device__ __forceinline__ float reduce16(float (&r)[16], int lane) {
@@ -448,23 +470,31 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
       const float vsl = (lane < P) ? s_vrow[lane] : 0.f, wsl = (lane < P) ? s_wrow[lane] : 0.f;
       float sig = 0.f;
       for (; kpass < nrb; kpass += BP * ncta) {
-        // warp w finishes row 32 k + w of each block of the pass (lane = panel column): y, w, x' and its norm partial
+        // warp w finishes row 32 k + w of each block of the pass (lane = panel column): y, w, x' and its norm partial.
+        // The 2 x BP lane-partial sums of the pass are reduced together (9 shuffles instead of 2 x BP x 5 dependent ones):
+        // afterwards lane 8 q holds y of row q, lane 8 q + 4 its xs.
+        float red8[8];
 #pragma unroll
         for (int q = 0; q < BP; ++q) {
+          const int k = kpass + q * ncta;
+          const float gq = (k < nrb) ? Gs[(q * 32 + lane) * 33 + warp] : 0.f;
+          red8[2 * q] = gq - (vr[q] * p1l + wr[q] * p2l);
+          red8[2 * q + 1] = vr[q] * wsl + wr[q] * vsl;
+        }
+        const float mine = reduce8(red8, lane);                    // value index bit2 | bit3 << 1 | bit4 << 2 of the lane
+#pragma unroll
+        for (int q = 0; q < BP; ++q) {
+          const float y = __shfl_sync(0xffffffffu, mine, 8 * q), xs = __shfl_sync(0xffffffffu, mine, 8 * q + 4);
           const int k = kpass + q * ncta, r = k * 32 + warp;
-          if (k >= nrb || r < s1 || r >= n) continue;             // warp-uniform
+          if (k >= nrb || r < s1 || r >= n || lane != 0) continue;
           const float v = TRD_VFIX(r, rw[q]);
-          const float y = warp_sum(Gs[(q * 32 + lane) * 33 + warp] - (vr[q] * p1l + wr[q] * p2l));
-          const float xs = warp_sum(vr[q] * wsl + wr[q] * vsl);
-          if (lane == 0) {
-            const float w = tau * (y - 0.5f * tau * ytv * v);
-            mt.Wp[r * NB + P] = w;
-            mt.Vp[r * NB + P] = v;
-            if (r > s1) {
-              const float x = ac[q] - xs - (v * w1 + w);          // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
-              col[r] = x;
-              if (r > s1 + 1) sig = fmaf(x, x, sig);
-            }
+          const float w = tau * (y - 0.5f * tau * ytv * v);
+          mt.Wp[r * NB + P] = w;
+          mt.Vp[r * NB + P] = v;
+          if (r > s1) {
+            const float x = ac[q] - xs - (v * w1 + w);             // panel column P: V[s+1][P] = 1, W[s+1][P] = w1
+            col[r] = x;
+            if (r > s1 + 1) sig = fmaf(x, x, sig);
           }
         }
         if (kpass + BP * ncta < nrb) {                   // another pass (small groups only): reload, regather
