@@ -91,7 +91,7 @@ __global__ void clamp_copy_kernel(const float* src, float* dst, int n, int* stat
 
 struct MatLayout {
   int n, np, nblk, nbt;
-  size_t A, VT, Vb, Q0, Q1, Vp, Wp, part, col, tau, d, e, cpart, bar, fscr, iscr, S, Tm, Y, Y2, slabY, slabS;
+  size_t A, VT, Vb, Q0, Q1, P, Vp, Wp, part, col, tau, d, e, cpart, bar, fscr, iscr, S, Tm, Y, Y2, slabY, slabS;
   int ksplit;      // split count of the longest reduction of the back-transformation (K = np)
 };
 
@@ -120,7 +120,7 @@ void make_layout(const int* n, int count, Layout& L) {
     MatLayout& m = L.m[i];
     m.n = n[i]; m.np = round_up(n[i], TRD_T); m.nblk = m.np / TRD_T; m.nbt = ceil_div(n[i], BT);
     const size_t sq = (size_t)m.np * m.np * sizeof(float);
-    m.A = take(sq + (size_t)m.np * BT * 4); m.VT = take(sq); m.Vb = take(sq + (size_t)m.np * BT * 4); m.Q0 = take(sq); m.Q1 = take(sq);
+    m.A = take(sq + (size_t)m.np * BT * 4); m.VT = take(sq); m.Vb = take(sq + (size_t)m.np * BT * 4); m.Q0 = take(sq); m.Q1 = take(sq); m.P = take(sq);
     m.ksplit = m.np > 1024 ? ceil_div(m.np, 512) : 1;
     m.Y = take((size_t)m.np * BT * 4); m.Y2 = take((size_t)m.np * BT * 4);
     m.slabY = take((size_t)m.ksplit * m.np * BT * 4);
@@ -130,7 +130,7 @@ void make_layout(const int* n, int count, Layout& L) {
     m.col = take((size_t)m.np * 4); m.tau = take((size_t)m.np * 4); m.d = take((size_t)m.np * 4); m.e = take((size_t)m.np * 4);
     m.cpart = take((size_t)grid * TRD_CP * 4);
     m.bar = take(256);
-    m.fscr = take((size_t)12 * m.n * 4); m.iscr = take((size_t)10 * m.n * 4);
+    m.fscr = take((size_t)12 * m.n * 4); m.iscr = take((size_t)12 * m.n * 4);
     m.S = take((size_t)m.nbt * BT * BT * 4); m.Tm = take((size_t)m.nbt * BT * BT * 4);
   }
   L.total = off;
@@ -267,6 +267,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     DcMat& d = dc[i];
     d.d = t.d; d.e = t.e; d.Q[0] = (float*)(base + m.Q0); d.Q[1] = (float*)(base + m.Q1);
     d.UT = t.A;                       // the working copy of F is dead after the tridiagonalisation
+    d.P = (float*)(base + m.P);
     d.fscr = (float*)(base + m.fscr); d.iscr = (int*)(base + m.iscr);
     d.n = m.n; d.ld = m.np; d.result_buf = 0;
     // inputs / zeroed state
@@ -442,8 +443,8 @@ extern "C" int kfac_experimental_stedc(const float* d_in, const float* e_in, int
   const int np = round_up(n, TRD_T);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  const size_t oQ0 = take((size_t)np * np * 4), oQ1 = take((size_t)np * np * 4), oUT = take((size_t)np * np * 4),
-               oD = take((size_t)np * 4), oE = take((size_t)np * 4), oF = take((size_t)12 * n * 4), oI = take((size_t)10 * n * 4),
+  const size_t oQ0 = take((size_t)np * np * 4), oQ1 = take((size_t)np * np * 4), oUT = take((size_t)np * np * 4), oP = take((size_t)np * np * 4),
+               oD = take((size_t)np * 4), oE = take((size_t)np * 4), oF = take((size_t)12 * n * 4), oI = take((size_t)12 * n * 4),
                oMat = take(sizeof(DcMat));
   const size_t pb = stedc_plan_bytes(&n, 1);
   const size_t oPlan = take(pb);
@@ -451,7 +452,7 @@ extern "C" int kfac_experimental_stedc(const float* d_in, const float* e_in, int
   char* base = (char*)ws;
   DcMat m;
   m.d = (float*)(base + oD); m.e = (float*)(base + oE); m.Q[0] = (float*)(base + oQ0); m.Q[1] = (float*)(base + oQ1);
-  m.UT = (float*)(base + oUT); m.fscr = (float*)(base + oF); m.iscr = (int*)(base + oI); m.n = n; m.ld = np; m.result_buf = 0;
+  m.UT = (float*)(base + oUT); m.P = (float*)(base + oP); m.fscr = (float*)(base + oF); m.iscr = (int*)(base + oI); m.n = n; m.ld = np; m.result_buf = 0;
   KFAC_CUDA(cudaMemcpyAsync(m.d, d_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
   KFAC_CUDA(cudaMemsetAsync(m.e, 0, (size_t)np * 4, s));
   if (n > 1) KFAC_CUDA(cudaMemcpyAsync(m.e, e_in, (size_t)(n - 1) * 4, cudaMemcpyDeviceToDevice, s));
@@ -465,7 +466,7 @@ extern "C" int kfac_experimental_stedc(const float* d_in, const float* e_in, int
 
 extern "C" size_t kfac_experimental_direct_workspace_bytes(int n) {
   const int np = (n + 63) / 64 * 64;
-  return (size_t)np * np * 4 * 4 + (size_t)np * 4096 + (1u << 22);
+  return (size_t)np * np * 4 * 5 + (size_t)np * 4096 + (1u << 22);
 }
 
 namespace kfac { int sytrd_profile(int on, unsigned long long* out16); }

@@ -46,8 +46,9 @@ struct DcMat {
   float* e;        // n   sub-diagonal (destroyed)
   float* Q[2];     // n x ld ping-pong eigenvector matrices (columns = eigenvectors); result in Q[result_buf]
   float* UT;       // n x ld workspace (rows = coefficient vectors of the merged eigenvectors)
+  float* P;        // n x ld workspace (non-deflated columns of Q_old, packed by type, for the large merges)
   float* fscr;     // 10 n floats of scratch
-  int* iscr;       // 8 n ints of scratch
+  int* iscr;       // 12 n ints of scratch
   int n, ld;
   int result_buf;
 };

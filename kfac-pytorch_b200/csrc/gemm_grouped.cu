@@ -29,6 +29,7 @@ struct alignas(128) GProb {
   int epi; const float* E; int64_t lde; const float* dg; const float* da; float damping;
   int64_t slab_stride;             // != 0: D is the slab base, split sp stores to D + sp * slab_stride
   int mode;                        // 0 store, 1 read-modify-write accumulate, 2 atomicAdd
+  const int* krange;               // device-side {first, end} k-block of the reduction (mode 2), or null
   float* peerD[7]; int npeer;
 };
 
@@ -57,8 +58,10 @@ struct GroupedPolicy {
     it.m0 = (tile / pr->tiles_n) * GBM;
     it.n0 = (tile % pr->tiles_n) * GBN;
     it.sp = sp;
-    it.kb0 = sp * pr->kb_per_split;
-    it.kb1 = min(pr->kb_total, it.kb0 + pr->kb_per_split);
+    int kb_lo = 0, kb_hi = pr->kb_total;
+    if (pr->krange) { kb_lo = max(0, pr->krange[0]); kb_hi = min(kb_hi, pr->krange[1]); }
+    it.kb0 = kb_lo + sp * pr->kb_per_split;
+    it.kb1 = min(kb_hi, it.kb0 + pr->kb_per_split);
     return it.kb1 > it.kb0;
   }
   __device__ static int num_kb(const Params&, const Item& it) { return it.kb1 - it.kb0; }
@@ -172,6 +175,10 @@ int launch_grouped_gemm(const GroupedGemm* probs, int count, void* ws, size_t ws
       return KFAC_ERR_BAD_ARG;
     }
     if (g.mode != 0 && (g.epi != EPI_NONE || g.npeer > 0)) { set_error("grouped gemm: accumulate modes need the plain epilogue"); return KFAC_ERR_BAD_ARG; }
+    if (g.krange && (g.mode != 2 || !grouped_gemm_tc_ok(g))) {
+      set_error("grouped gemm: a device-side k range needs the atomic mode on the tensor-core path");
+      return KFAC_ERR_BAD_ARG;
+    }
     if (!grouped_gemm_tc_ok(g)) {
       // small / unaligned problems: one SIMT launch each (fp32, no split needed)
       GemmArgs a{};
@@ -200,7 +207,7 @@ int launch_grouped_gemm(const GroupedGemm* probs, int count, void* ws, size_t ws
     p.kb_total = ceil_div(g.K, GBK);
     p.kb_per_split = ceil_div(p.kb_total, splits);
     p.splits = ceil_div(p.kb_total, p.kb_per_split);
-    p.mode = g.mode;
+    p.mode = g.mode; p.krange = g.krange;
     if (p.splits > 1 && g.mode == 2) {
       p.D = g.D; p.slab_stride = 0;
     } else if (p.splits > 1) {

@@ -15,6 +15,8 @@ struct GroupedGemm {
   int splits;                      // > 1: split-K -- deterministic through `slab` (plain epilogue, no peers), or mode 2
   float* slab; int64_t slab_stride;
   int mode;                        // 0: D = ..., 1: D += ... (read-modify-write, splits == 1), 2: atomicAdd into D (caller zeroes D)
+  const int* krange;               // optional (mode 2 only): DEVICE pointer to {first, end} k-block (32 columns of K) the product
+                                   // runs over, read by the kernel -- for reductions whose extent is only known on the device
 };
 
 size_t grouped_gemm_ws_bytes(int count);

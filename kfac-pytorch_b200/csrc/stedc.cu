@@ -10,7 +10,11 @@
 //       secular  (one warp per root: bracketing bisection on |mu| with geometric steps, pole-shifted origin)
 //       zhat     (one warp per entry: Loewner product)
 //       rank + build (final order; rows of U~^T: new eigenvectors in the basis of the old columns)
-//       GEMM     Q_new = Q_old U~ on the tcgen05 engine (one launch per merge, dense m x m x m)
+//       GEMM     Q_new = Q_old U~ on the tcgen05 engine, ONE grouped launch per level.  Merges of more than
+//                DENSE_MAX rows use the structure LAPACK's slaed2/slaed3 use: only the k non-deflated columns of
+//                Q_old enter the product (packed as [upper-only | mixed | lower-only] into P), the upper and lower
+//                row halves are two problems over the column ranges they can see, and the deflated eigenvectors
+//                are copied.  k is only known on the device: the kernel reads its k-block range from memory.
 // Eigenvalues come out ascending, eigenvectors as columns of Q[result_buf].
 #include "eigh_direct.cuh"
 
@@ -22,6 +26,7 @@ namespace kfac {
 namespace {
 
 constexpr int LEAF = 64;
+constexpr int DENSE_MAX = 1024;           // merges up to this size multiply the full m x m x m product
 constexpr float EPS = 5.9604645e-8f;      // relative machine epsilon (LAPACK slamch('E'))
 
 struct DcMerge { int mat, lo, mid, hi, src; };   // src: buffer holding the children's eigenvectors
@@ -30,7 +35,9 @@ struct DcCut { int mat, pos; };
 
 // scratch arrays (offsets in units of n)
 enum { F_DL = 0, F_W, F_MU, F_LAM, F_ZHAT, F_DTMP, F_VALS, F_RC, F_RS, F_RHO, F_COUNT };
-enum { I_NDCOL = 0, I_DFCOL, I_ORIG, I_INV, I_ROTA, I_ROTB, I_K, I_NROT, I_COUNT };
+enum { I_NDCOL = 0, I_DFCOL, I_ORIG, I_INV, I_ROTA, I_ROTB, I_K, I_NROT, I_CPOS, I_CSRC, I_KR, I_COUNT };
+// I_CPOS[i]: packed position of non-deflated entry i; I_CSRC[c]: column of Q_old packed at c;
+// I_KR[0..3]: k-block ranges {upper begin, upper end, lower begin, lower end} of the two structured products
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -145,6 +152,7 @@ __global__ void __launch_bounds__(1024) dc_deflate_kernel(const DcMat* mats, con
   float* sd = rz + m;              // sorted
   float* sz = sd + m;
   int* ssrc = reinterpret_cast<int*>(sz + m);
+  int* ctype = ssrc + m;           // per column of Q_old: 1 = non-zero in the upper rows only, 3 = lower only, 2 = both
   __shared__ float redf[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* Q = mt.Q[mg.src];
@@ -157,6 +165,7 @@ __global__ void __launch_bounds__(1024) dc_deflate_kernel(const DcMat* mats, con
     const float zv = (i < n1 ? Q[(int64_t)(mg.mid - 1) * mt.ld + mg.lo + i] : sgn * Q[(int64_t)mg.mid * mt.ld + mg.lo + i]) *
                      0.70710678118654752f;
     rd[i] = dv; rz[i] = zv;
+    ctype[i] = i < n1 ? 1 : 3;
     dmax = fmaxf(dmax, fabsf(dv));
     zmax = fmaxf(zmax, fabsf(zv));
   }
@@ -188,11 +197,22 @@ __global__ void __launch_bounds__(1024) dc_deflate_kernel(const DcMat* mats, con
   int* dfcol = is + (int64_t)I_DFCOL * n + mg.lo;
   int* rota = is + (int64_t)I_ROTA * n + mg.lo;
   int* rotb = is + (int64_t)I_ROTB * n + mg.lo;
+  int* cpos = is + (int64_t)I_CPOS * n + mg.lo;
+  int* csrc = is + (int64_t)I_CSRC * n + mg.lo;
   const float tol = 8.f * EPS * fmaxf(dmax, zmax);
   if (tid == 0) {
     int k = 0, nd = 0, nrot = 0;
-    // deflated values are written to rd[] (raw arrays are free now) in scan order, columns to rz-as-int
+    int kt[4] = {0, 0, 0, 0};        // non-deflated columns per type
+    // deflated values are written to rd[] (raw arrays are free now) in scan order, columns to rz-as-int;
+    // the type and column of the non-deflated entries are kept at the far end of the same arrays (nd + k <= m)
     int* dcol_tmp = reinterpret_cast<int*>(rz);
+    int* ktype_tmp = reinterpret_cast<int*>(rd);
+    auto emit = [&](int pj) {
+      const int col = ssrc[pj], t = ctype[col];
+      dl[k] = sd[pj]; w[k] = sz[pj]; ndcol[k] = col;
+      ktype_tmp[m - 1 - k] = t; dcol_tmp[m - 1 - k] = col; ++kt[t];
+      ++k;
+    };
     if (rho * zmax <= tol) {
       for (int j = 0; j < m; ++j) { rd[nd] = sd[j]; dcol_tmp[nd] = ssrc[j]; ++nd; }
     } else {
@@ -208,17 +228,31 @@ __global__ void __launch_bounds__(1024) dc_deflate_kernel(const DcMat* mats, con
         if (fabsf(t * c * s) <= tol) {
           sz[j] = tau; sz[pj] = 0.f;
           rota[nrot] = ssrc[pj]; rotb[nrot] = ssrc[j]; rc[nrot] = c; rs[nrot] = s; ++nrot;
+          if (ctype[ssrc[pj]] != ctype[ssrc[j]]) ctype[ssrc[j]] = 2;      // the surviving column now mixes both halves
           const float dp = sd[pj], dj = sd[j];
           sd[j] = dp * s * s + dj * c * c;
           sd[pj] = dp * c * c + dj * s * s;
           rd[nd] = sd[pj]; dcol_tmp[nd] = ssrc[pj]; ++nd;
           pj = j;
         } else {
-          dl[k] = sd[pj]; w[k] = sz[pj]; ndcol[k] = ssrc[pj]; ++k;
+          emit(pj);
           pj = j;
         }
       }
-      if (pj >= 0) { dl[k] = sd[pj]; w[k] = sz[pj]; ndcol[k] = ssrc[pj]; ++k; }
+      if (pj >= 0) emit(pj);
+    }
+    // packed order of the non-deflated columns: [upper only | mixed | lower only]
+    {
+      int off[4] = {0, 0, kt[1], kt[1] + kt[2]};
+      for (int i = 0; i < k; ++i) {
+        const int t = ktype_tmp[m - 1 - i], c = off[t]++;
+        cpos[i] = c; csrc[c] = dcol_tmp[m - 1 - i];
+      }
+      int* kr = is + (int64_t)I_KR * n + mg.lo;
+      kr[0] = 0; kr[1] = (kt[1] + kt[2] + 31) / 32;          // upper rows see types 1 and 2
+      kr[2] = kt[1] / 32; kr[3] = (k + 31) / 32;             // lower rows see types 2 and 3
+      if (kt[1] + kt[2] == 0) kr[1] = 0;
+      if (kt[2] + kt[3] == 0) kr[3] = kr[2];
     }
     is[(int64_t)I_K * n + mg.lo] = k;
     is[(int64_t)I_NROT * n + mg.lo] = nrot;
@@ -260,6 +294,43 @@ __global__ void __launch_bounds__(256) dc_rotate_kernel(const DcMat* mats, const
     cur = b;
   }
   if (cur >= 0) row[cur] = yb;
+}
+
+// ------------------------------------------------------------------ non-deflated columns of Q_old, packed by type
+__global__ void __launch_bounds__(256) dc_pack_kernel(const DcMat* mats, const DcMerge* merges) {
+  const DcMerge mg = merges[blockIdx.y];
+  const DcMat& mt = mats[mg.mat];
+  const int m = mg.hi - mg.lo, n = mt.n;
+  if (m <= DENSE_MAX) return;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= m) return;
+  const int k = mt.iscr[(int64_t)I_K * n + mg.lo];
+  const int kpad = (k + 31) & ~31;                            // the last k-block of the products is zero filled
+  const int* csrc = mt.iscr + (int64_t)I_CSRC * n + mg.lo;
+  const float* src = mt.Q[mg.src] + (int64_t)(mg.lo + r) * mt.ld + mg.lo;
+  float* dst = mt.P + (int64_t)(mg.lo + r) * mt.ld + mg.lo;
+  for (int c = lane; c < kpad; c += 32) dst[c] = c < k ? src[csrc[c]] : 0.f;
+}
+
+// deflated eigenvectors are columns of Q_old: copy them to their final positions (after the structured product)
+__global__ void __launch_bounds__(256) dc_copy_deflated_kernel(const DcMat* mats, const DcMerge* merges) {
+  const DcMerge mg = merges[blockIdx.y];
+  const DcMat& mt = mats[mg.mat];
+  const int m = mg.hi - mg.lo, n = mt.n;
+  if (m <= DENSE_MAX) return;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= m) return;
+  const int k = mt.iscr[(int64_t)I_K * n + mg.lo];
+  const int* inv = mt.iscr + (int64_t)I_INV * n + mg.lo;
+  const int* dfcol = mt.iscr + (int64_t)I_DFCOL * n + mg.lo;
+  const float* src = mt.Q[mg.src] + (int64_t)(mg.lo + r) * mt.ld + mg.lo;
+  float* dst = mt.Q[mg.src ^ 1] + (int64_t)(mg.lo + r) * mt.ld + mg.lo;
+  for (int p = lane; p < m; p += 32) {
+    const int s = inv[p];
+    if (s >= k) dst[p] = src[dfcol[s - k]];
+  }
 }
 
 // ------------------------------------------------------------------ secular equation, one warp per root
@@ -378,16 +449,18 @@ __global__ void __launch_bounds__(256) dc_build_kernel(const DcMat* mats, const 
   const int k = mt.iscr[(int64_t)I_K * n + mg.lo];
   const int src = mt.iscr[(int64_t)I_INV * n + mg.lo + p];
   float* row = mt.UT + (int64_t)(mg.lo + p) * mt.ld + mg.lo;
-  for (int c = lane; c < m; c += 32) row[c] = 0.f;
+  const bool packed = m > DENSE_MAX;          // coefficients over the packed non-deflated columns only (dc_pack_kernel)
+  const int width = packed ? ((k + 31) & ~31) : m;
+  for (int c = lane; c < width; c += 32) row[c] = 0.f;
   __syncwarp();
   if (lane == 0) mt.fscr[(int64_t)F_DTMP * n + mg.lo + p] = mt.fscr[(int64_t)F_VALS * n + mg.lo + src];
   if (src >= k) {
-    if (lane == 0) row[mt.iscr[(int64_t)I_DFCOL * n + mg.lo + src - k]] = 1.f;
+    if (lane == 0 && !packed) row[mt.iscr[(int64_t)I_DFCOL * n + mg.lo + src - k]] = 1.f;
     return;
   }
   const float* dl = mt.fscr + (int64_t)F_DL * n + mg.lo;
   const float* zh = mt.fscr + (int64_t)F_ZHAT * n + mg.lo;
-  const int* ndcol = mt.iscr + (int64_t)I_NDCOL * n + mg.lo;
+  const int* ndcol = mt.iscr + (int64_t)(packed ? I_CPOS : I_NDCOL) * n + mg.lo;
   const float muj = mt.fscr[(int64_t)F_MU * n + mg.lo + src];
   const float dlo = dl[mt.iscr[(int64_t)I_ORIG * n + mg.lo + src]];
   float ss = 0.f;
@@ -458,7 +531,7 @@ size_t stedc_plan_bytes(const int* n, int count) {
   size_t widest = 1;
   for (auto& l : pl.levels) widest = std::max(widest, l.size());
   return align_up(sizeof(DcCut) * pl.cuts.size() + 256, 256) + align_up(sizeof(DcLeaf) * pl.leaves.size() + 256, 256) +
-         align_up(sizeof(DcMerge) * merges + 256 * (pl.levels.size() + 1), 256) + align_up(grouped_gemm_ws_bytes((int)widest), 256);
+         align_up(sizeof(DcMerge) * merges + 256 * (pl.levels.size() + 1), 256) + align_up(grouped_gemm_ws_bytes(2 * (int)widest), 256);
 }
 
 int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, int* status, cudaStream_t s) {
@@ -475,7 +548,7 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
   for (auto& l : pl.levels) d_levels.push_back((DcMerge*)take(sizeof(DcMerge) * l.size()));
   size_t widest = 1;
   for (auto& l : pl.levels) widest = std::max(widest, l.size());
-  const size_t gws_bytes = grouped_gemm_ws_bytes((int)widest);
+  const size_t gws_bytes = grouped_gemm_ws_bytes(2 * (int)widest);
   void* gws = take(gws_bytes);
   if (off > plan_bytes) { set_error("stedc: plan workspace too small (%zu < %zu)", plan_bytes, off); return KFAC_ERR_WORKSPACE; }
   if (!pl.cuts.empty())
@@ -506,12 +579,16 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
     const int nm = (int)lv.size();
     int mmax = 0;
     for (auto& mg : lv) mmax = std::max(mmax, mg.hi - mg.lo);
-    const size_t dsmem = (size_t)mmax * 5 * sizeof(float);
+    const size_t dsmem = (size_t)mmax * 6 * sizeof(float);
     if (dsmem > 200 * 1024) { set_error("stedc: merge of %d rows exceeds the shared-memory sort", mmax); return KFAC_ERR_UNSUPPORTED; }
     dc_deflate_kernel<<<nm, 1024, dsmem, s>>>(d_mats, d_levels[l]);
     KFAC_LAUNCH_CHECK();
     dc_rotate_kernel<<<dim3(ceil_div(mmax, 256), nm), 256, 0, s>>>(d_mats, d_levels[l]);
     KFAC_LAUNCH_CHECK();
+    if (mmax > DENSE_MAX) {
+      dc_pack_kernel<<<dim3(ceil_div(mmax, 8), nm), 256, 0, s>>>(d_mats, d_levels[l]);
+      KFAC_LAUNCH_CHECK();
+    }
     dc_secular_kernel<<<dim3(ceil_div(mmax, 8), nm), 256, 0, s>>>(d_mats, d_levels[l]);
     KFAC_LAUNCH_CHECK();
     dc_zhat_kernel<<<dim3(ceil_div(mmax, 8), nm), 256, 0, s>>>(d_mats, d_levels[l]);
@@ -527,18 +604,31 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
     std::vector<GroupedGemm> gg;
     for (auto& mg : lv) {
       const DcMat& mt = h_mats[mg.mat];
-      const int m = mg.hi - mg.lo;
+      const int m = mg.hi - mg.lo, n1 = mg.mid - mg.lo;
       const int64_t o = (int64_t)mg.lo * mt.ld + mg.lo;
       GroupedGemm g{};
-      g.A = mt.Q[mg.src] + o; g.lda = mt.ld; g.B = mt.UT + o; g.ldb = mt.ld; g.D = mt.Q[mg.src ^ 1] + o; g.ldd = mt.ld;
-      g.M = m; g.N = m; g.K = m; g.alpha = 1.f; g.epi = EPI_NONE; g.splits = 1;
-      if (m > 1024 && grouped_gemm_tc_ok(g)) {
+      g.lda = mt.ld; g.B = mt.UT + o; g.ldb = mt.ld; g.ldd = mt.ld;
+      g.N = m; g.K = m; g.alpha = 1.f; g.epi = EPI_NONE; g.splits = 1;
+      if (m > DENSE_MAX) {
+        // structured: packed non-deflated columns, upper and lower row halves over the k-block ranges written by the
+        // deflation kernel (I_KR); deflated eigenvectors are copied afterwards
+        KFAC_CUDA(cudaMemset2DAsync(mt.Q[mg.src ^ 1] + o, (size_t)mt.ld * 4, 0, (size_t)m * 4, (size_t)m, s));
         g.splits = ceil_div(m, 512); g.mode = 2;
-        KFAC_CUDA(cudaMemset2DAsync(g.D, (size_t)mt.ld * 4, 0, (size_t)m * 4, (size_t)m, s));
+        const int* kr = mt.iscr + (int64_t)I_KR * mt.n + mg.lo;
+        g.A = mt.P + o; g.D = mt.Q[mg.src ^ 1] + o; g.M = n1; g.krange = kr;
+        gg.push_back(g);
+        g.A = mt.P + o + (int64_t)n1 * mt.ld; g.D = mt.Q[mg.src ^ 1] + o + (int64_t)n1 * mt.ld; g.M = m - n1; g.krange = kr + 2;
+        gg.push_back(g);
+      } else {
+        g.A = mt.Q[mg.src] + o; g.D = mt.Q[mg.src ^ 1] + o; g.M = m;
+        gg.push_back(g);
       }
-      gg.push_back(g);
     }
     { const int rc = launch_grouped_gemm(gg.data(), (int)gg.size(), gws, gws_bytes, s); if (rc) return rc; }
+    if (mmax > DENSE_MAX) {
+      dc_copy_deflated_kernel<<<dim3(ceil_div(mmax, 8), nm), 256, 0, s>>>(d_mats, d_levels[l]);
+      KFAC_LAUNCH_CHECK();
+    }
   }
   for (int i = 0; i < count; ++i) h_mats[i].result_buf = pl.result_buf[i];
   return KFAC_OK;

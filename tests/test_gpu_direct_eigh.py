@@ -89,7 +89,9 @@ def test_sytrd(lib, n, ncta, kind):
 
 
 @pytest.mark.parametrize('n,kind', [(65, 'rand'), (100, 'rand'), (128, 'rand'), (200, 'kfac'), (576, 'kfac'), (1000, 'rand'),
-                                    (2049, 'kfac'), (1024, 'equal'), (4608, 'kfac'), (300, 'zero_e')])
+                                    (2049, 'kfac'), (1024, 'equal'), (4608, 'kfac'), (300, 'zero_e'),
+                                    # merges of more than 1024 rows take the structured (packed, two-halves) product
+                                    (2304, 'rand'), (2500, 'equal'), (3000, 'zero_e'), (2100, 'glued'), (4608, 'rand')])
 def test_stedc(lib, n, kind):
     dev = torch.device('cuda:0')
     g = torch.Generator().manual_seed(n)
@@ -103,6 +105,9 @@ def test_stedc(lib, n, kind):
     elif kind == 'zero_e':
         d = torch.rand(n, generator=g)
         e = torch.zeros(n - 1)
+    elif kind == 'glued':   # pairs of nearly equal eigenvalues on both sides of every cut: many deflating rotations
+        d = (torch.arange(n) % 37).float() * 0.1 + 1e-7 * torch.randn(n, generator=g)
+        e = 1e-4 * torch.rand(n - 1, generator=g)
     else:   # tridiagonal of a K-FAC-like factor (fp64 Householder on the host side of the test)
         F = sym(n, n, 'kfac').double()
         import scipy.linalg
