@@ -91,6 +91,43 @@ __device__ __forceinline__ float reduce8(float (&r)[8], int lane) {
   return r[0];
 }
 
+// sums of 8 per-lane values over each 16-lane half of the warp with 8 shuffles: afterwards every lane holds the sum
+// (over its half) of value number (lane >> 1) & 7 bit-reversed, i.e. ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)
+__device__ __forceinline__ float reduce8h(float (&r)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = (lane & 8) ? r[i + 4] : r[i], send = (lane & 8) ? r[i] : r[i + 4];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = (lane & 4) ? r[i + 2] : r[i], send = (lane & 4) ? r[i] : r[i + 2];
+    r[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float keep = (lane & 2) ? r[1] : r[0], send = (lane & 2) ? r[0] : r[1];
+    r[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+  return r[0];
+}
+
+// packed fp32 pairs (FFMA2 / FMUL2 of sm_100): one issue slot for two fused multiply-adds
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  memcpy(&ra, &a, 8); memcpy(&rb, &b, 8); memcpy(&rc, &c, 8);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d; memcpy(&d, &rd, 8);
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  memcpy(&ra, &a, 8); memcpy(&rb, &b, 8);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d; memcpy(&d, &rd, 8);
+  return d;
+}
+
 // sums of 16 per-lane values over the warp with 16 shuffles: afterwards every lane holds the complete sum of value
 // number (lane >> 1) & 15
 __device__ __forceinline__ float reduce16(float (&r)[16], int lane) {
@@ -293,45 +330,58 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         if (vb) vb[(int64_t)r * TRD_BT] = v;
       }
     }
-    // symmetric product with the lower tiles of this sub-group (128 threads: a warp takes 16 rows of the tile)
+    // symmetric product with the lower tiles of this sub-group (128 threads: a warp takes 16 rows of the tile; its lower
+    // half-warp rows 0..7, the upper one rows 8..15; a lane holds 4 adjacent columns of 8 rows).  The phase is bound by
+    // issue slots, not by bandwidth: 128-bit loads, packed fp32 pairs and half-warp reductions keep the count down.
     float vav = 0.f;
     {
       float* cs = stage + sg8 * (4 * T);             // column partial sums: [4 warps][64]
       const int st_tid = tid & 127;
+      const int hl = lane & 15, h8 = (lane >> 4) * 8;
       for (int ti = 0; ti < ntile8; ++ti) {
         const int I = tlist8[ti].x, J = tlist8[ti].y;
         if (J < b0) break;                           // the active tiles are a prefix of the list
-        const int rb = I * T + sw4 * 16, c0 = J * T + 2 * lane;
+        const int rb = I * T + sw4 * 16 + h8, c0 = J * T + 4 * hl;
         const float* ap = A + (int64_t)rb * np + c0;
-        float2 a[16];
+        float4 a[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a[k] = __ldcg(reinterpret_cast<const float2*>(ap + (int64_t)k * np));
-        const float rj0 = TRD_RAW(c0), rj1 = TRD_RAW(c0 + 1);
-        const int ri_r = rb + (lane & 15);
+        for (int k = 0; k < 8; ++k) a[k] = __ldcg(reinterpret_cast<const float4*>(ap + (int64_t)k * np));
+        const float4 rj = __ldcg(reinterpret_cast<const float4*>(col + c0));     // col has np >= c0 + 4 entries
+        const int ri_r = rb + (lane & 7);
         const float ri = TRD_RAW(ri_r);
-        const float vj0 = TRD_VFIX(c0, rj0), vj1 = TRD_VFIX(c0 + 1, rj1);
+        float2 vj01, vj23;
+        vj01.x = (c0 > s1 && c0 < n) ? rj.x * scal : (c0 == s1 ? 1.f : 0.f);
+        vj01.y = (c0 + 1 > s1 && c0 + 1 < n) ? rj.y * scal : (c0 + 1 == s1 ? 1.f : 0.f);
+        vj23.x = (c0 + 2 > s1 && c0 + 2 < n) ? rj.z * scal : (c0 + 2 == s1 ? 1.f : 0.f);
+        vj23.y = (c0 + 3 > s1 && c0 + 3 < n) ? rj.w * scal : (c0 + 3 == s1 ? 1.f : 0.f);
         const float vi_l = TRD_VFIX(ri_r, ri);
-        float rs[16];
-        float c0acc = 0.f, c1acc = 0.f;
+        float rs[8];
+        float2 c01 = make_float2(0.f, 0.f), c23 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float vi = __shfl_sync(0xffffffffu, vi_l, k);
-          rs[k] = fmaf(a[k].x, vj0, a[k].y * vj1);
-          c0acc = fmaf(a[k].x, vi, c0acc);
-          c1acc = fmaf(a[k].y, vi, c1acc);
+        for (int k = 0; k < 8; ++k) {
+          const float vi = __shfl_sync(0xffffffffu, vi_l, (lane & 16) + k);
+          const float2 vi2 = make_float2(vi, vi);
+          const float2 a01 = make_float2(a[k].x, a[k].y), a23 = make_float2(a[k].z, a[k].w);
+          const float2 t = fma2(a23, vj23, mul2(a01, vj01));
+          rs[k] = t.x + t.y;
+          c01 = fma2(a01, vi2, c01);
+          c23 = fma2(a23, vi2, c23);
         }
-        const float tot = reduce16(rs, lane);
-        const int rid = (lane >> 1) & 15;
-        const float vi_r = __shfl_sync(0xffffffffu, vi_l, rid);
+        const float tot = reduce8h(rs, lane);
+        const int rid = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        const float vi_r = __shfl_sync(0xffffffffu, vi_l, (lane & 16) + rid);
         if ((lane & 1) == 0) {
           mt.part[(int64_t)J * np + rb + rid] = tot;
           const float t = tot * vi_r;
           vav += (I == J) ? t : 2.f * t;
         }
         if (I != J) {
+          c01.x += __shfl_xor_sync(0xffffffffu, c01.x, 16);
+          c01.y += __shfl_xor_sync(0xffffffffu, c01.y, 16);
+          c23.x += __shfl_xor_sync(0xffffffffu, c23.x, 16);
+          c23.y += __shfl_xor_sync(0xffffffffu, c23.y, 16);
           sub_sync8(sg8);                            // previous tile's readers are done with cs
-          cs[sw4 * T + 2 * lane] = c0acc;
-          cs[sw4 * T + 2 * lane + 1] = c1acc;
+          if (lane < 16) *reinterpret_cast<float4*>(&cs[sw4 * T + 4 * hl]) = make_float4(c01.x, c01.y, c23.x, c23.y);
           sub_sync8(sg8);
           if (st_tid < T) {
             const float t = (cs[st_tid] + cs[T + st_tid]) + (cs[2 * T + st_tid] + cs[3 * T + st_tid]);
