@@ -77,10 +77,14 @@ int kfac_factor_conv2d_input(const void* x, int dtype, int batch, int C, int H,
                              void* ws, size_t ws_bytes, void* stream);
 
 /* replaces Conv2dModuleHelper.get_g_factor (modules.py:180-192):
- * g is (batch, C, Ho, Wo); acc (C x C) += scale * sum_n Y_n Y_n^T. */
+ * g is (batch, C, Ho, Wo); acc (C x C) += scale * sum_n Y_n Y_n^T.
+ * ws (optional, kfac_factor_conv2d_gradout_workspace_bytes): maps whose rows are not
+ * 16-byte multiples (7 x 7) are packed there for the tensor-core SYRK; without it they
+ * take the SIMT kernel. */
+size_t kfac_factor_conv2d_gradout_workspace_bytes(int batch, int C, int Ho, int Wo);
 int kfac_factor_conv2d_gradout(const void* g, int dtype, int batch, int C,
                                int Ho, int Wo, float scale, float* acc,
-                               void* stream);
+                               void* ws, size_t ws_bytes, void* stream);
 
 /* K4: replaces KFACBaseLayer.update_{a,g}_factor (layers/base.py:375-405) and
  * the symmetrisation of get_cov (utils.py:57):

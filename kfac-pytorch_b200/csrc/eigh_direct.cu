@@ -142,7 +142,7 @@ void make_layout(const int* n, int count, Layout& L) {
 //   T0 + T1 n            barriers, dependent cross-CTA loads, the serial vector phases
 //   (B n^2 + GA n) / C   tile products of the trailing matrix (averaged over its shrinking size) + row work
 //   DE log2 C            barrier and cross-CTA reduction cost growing with the group
-constexpr double T0 = 7.19e-6, T1 = 2.46e-10, BETA = 1.265e-11, GAMMA = 2.09e-8, DELTA = 2.91e-7, EPS = -1.66e-6;
+constexpr double T0 = 7.78e-6, T1 = 4.7e-11, BETA = 1.144e-11, GAMMA = 2.06e-8, DELTA = 2.03e-7, EPS = -2.62e-6;
 double job_time(int n, int C) {
   return (double)n * (T0 + T1 * n + (BETA * (double)n * n + GAMMA * n + EPS) / C + DELTA * std::log2((double)C));
 }

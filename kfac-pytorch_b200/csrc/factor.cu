@@ -139,28 +139,37 @@ struct Im2colArgs {
   int ones;        // append a feature row of ones
   int64_t ld;      // leading dimension of the feature-major output (>= rows, multiple of 4)
 };
+// grid (ceil(ld / 4 / 256), features [+ 1]): a thread writes 4 consecutive samples of one feature row with one 16-byte
+// store; the (image, ho, wo) decomposition is done once per thread in 32-bit arithmetic and advanced incrementally
+// (the element-wise version spent its time in 64-bit divisions: 480 us for a 231 MB matrix, now bandwidth bound)
 template <typename T>
-__global__ void im2col_kernel(Im2colArgs a) {
+__global__ void __launch_bounds__(256) im2col_kernel(Im2colArgs a) {
   const int64_t rows = (int64_t)a.batch * a.Ho * a.Wo;
   const int nfeat = a.C * a.kh * a.kw;
-  const int64_t total = a.ld * (nfeat + a.ones);
-  const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = idx % a.ld;
-    const int f = (int)(idx / a.ld);
-    if (row >= rows) { a.out[idx] = 0.f; continue; }
-    if (f >= nfeat) { a.out[idx] = 1.f; continue; }
-    const int wo = (int)(row % a.Wo);
-    const int ho = (int)((row / a.Wo) % a.Ho);
-    const int n = (int)(row / ((int64_t)a.Wo * a.Ho));
+  const int f = blockIdx.y;
+  const int64_t r4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (r4 >= a.ld) return;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (f >= nfeat) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (r4 + k < rows) ? 1.f : 0.f;
+  } else if (r4 < rows) {
+    const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
     const int j = f % a.kw, i = (f / a.kw) % a.kh, c = f / (a.kw * a.kh);
-    const int h = ho * a.sh + i - a.ph, w = wo * a.sw + j - a.pw;
-    float v = 0.f;
-    if (h >= 0 && h < a.H && w >= 0 && w < a.W)
-      v = to_float<T>(x[(((int64_t)n * a.C + c) * a.H + h) * a.W + w]);
-    a.out[idx] = v;
+    const unsigned row = (unsigned)r4;                    // rows < 2^31 (checked by the caller)
+    int wo = (int)(row % (unsigned)a.Wo);
+    const unsigned t = row / (unsigned)a.Wo;
+    int ho = (int)(t % (unsigned)a.Ho), n = (int)(t / (unsigned)a.Ho);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (r4 + k < rows) {
+        const int h = ho * a.sh + i - a.ph, w = wo * a.sw + j - a.pw;
+        if (h >= 0 && h < a.H && w >= 0 && w < a.W) v[k] = to_float<T>(x[(((int64_t)n * a.C + c) * a.H + h) * a.W + w]);
+      }
+      if (++wo == a.Wo) { wo = 0; if (++ho == a.Ho) { ho = 0; ++n; } }
+    }
   }
+  *reinterpret_cast<float4*>(a.out + (int64_t)f * a.ld + r4) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // X (rows x feat, sample-major, any dtype) -> out (feat [+1 ones row]) x ld, feature-major fp32
@@ -324,7 +333,9 @@ extern "C" int kfac_factor_linear(const void* x, int dtype, int64_t rows, int fe
 extern "C" size_t kfac_factor_conv2d_input_workspace_bytes(int batch, int C, int H, int W, int kh,
                                                            int kw, int sh, int sw, int ph, int pw,
                                                            int append_ones) {
-  if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0) return 0;
+  // 1x1 / stride 1 reads the NCHW input in place -- unless its rows (H*W floats) are not 16-byte multiples
+  // (7 x 7 maps): TMA cannot address those, so they are packed like an im2col matrix
+  if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0 && (((int64_t)H * W) % 4 == 0 || C < 64)) return 0;
   const int64_t Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
   const int64_t ld = ((int64_t)batch * Ho * Wo + 3) / 4 * 4;
   return (size_t)ld * ((size_t)C * kh * kw + (append_ones ? 1 : 0)) * sizeof(float);
@@ -342,7 +353,7 @@ extern "C" int kfac_factor_conv2d_input(const void* x, int dtype, int batch, int
   KFAC_CHECK_ARG(Ho > 0 && Wo > 0, "empty output");
   CovArgs a{};
   a.ones = append_ones ? 1 : 0; a.scale = scale; a.acc = acc;
-  if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0) {
+  if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0 && (((int64_t)H * W) % 4 == 0 || C < 64)) {
     // 1x1 / stride 1: the NCHW input already is a feature-major (C x HW) matrix per image
     a.x = x; a.ld = (int64_t)H * W; a.batch_stride = (int64_t)C * H * W;
     a.rows = H * W; a.batch = batch; a.feat = C;
@@ -357,8 +368,8 @@ extern "C" int kfac_factor_conv2d_input(const void* x, int dtype, int batch, int
   KFAC_CHECK_ARG(rows < (1ll << 31), "rows overflow");
   const int64_t ld = (rows + 3) / 4 * 4;
   Im2colArgs ia{x, (float*)ws, batch, C, H, W, kh, kw, sh, sw, ph, pw, Ho, Wo, a.ones, ld};
-  const int64_t total = ld * ((int64_t)C * kh * kw + a.ones);
-  const int grid = grid_for(total) * 4;
+  KFAC_CHECK_ARG((int64_t)C * kh * kw + a.ones <= 65535, "conv2d_input: more than 65535 features");
+  const dim3 grid((unsigned)ceil_div(ld / 4, 256), (unsigned)(C * kh * kw + a.ones));
   if (dtype == KFAC_F32) im2col_kernel<float><<<grid, 256, 0, s>>>(ia);
   else if (dtype == KFAC_F16) im2col_kernel<__half><<<grid, 256, 0, s>>>(ia);
   else if (dtype == KFAC_BF16) im2col_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(ia);
@@ -370,10 +381,37 @@ extern "C" int kfac_factor_conv2d_input(const void* x, int dtype, int batch, int
   return launch_cov<true>(a, KFAC_F32, s);
 }
 
+extern "C" size_t kfac_factor_conv2d_gradout_workspace_bytes(int batch, int C, int Ho, int Wo) {
+  // maps whose rows (Ho*Wo floats) are not 16-byte multiples (7 x 7) are packed into an aligned feature-major
+  // matrix for the tcgen05 SYRK; everything else is read in place
+  if (((int64_t)Ho * Wo) % 4 == 0 || C < 64) return 0;
+  const int64_t ld = ((int64_t)batch * Ho * Wo + 3) / 4 * 4;
+  return (size_t)ld * (size_t)C * sizeof(float);
+}
+
 extern "C" int kfac_factor_conv2d_gradout(const void* g, int dtype, int batch, int C, int Ho, int Wo,
-                                          float scale, float* acc, void* stream) {
+                                          float scale, float* acc, void* ws, size_t ws_bytes, void* stream) {
   KFAC_CHECK_ARG(g && acc, "null pointer");
   KFAC_CHECK_ARG(batch > 0 && C > 0 && Ho > 0 && Wo > 0, "geometry");
+  const size_t need = kfac_factor_conv2d_gradout_workspace_bytes(batch, C, Ho, Wo);
+  if (need > 0 && ws && ws_bytes >= need) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t rows = (int64_t)batch * Ho * Wo;
+    KFAC_CHECK_ARG(rows < (1ll << 31), "rows overflow");
+    const int64_t ld = (rows + 3) / 4 * 4;
+    Im2colArgs ia{g, (float*)ws, batch, C, Ho, Wo, 1, 1, 1, 1, 0, 0, Ho, Wo, 0, ld};
+    KFAC_CHECK_ARG(C <= 65535, "conv2d_gradout: more than 65535 channels");
+    const dim3 grid((unsigned)ceil_div(ld / 4, 256), (unsigned)C);
+    if (dtype == KFAC_F32) im2col_kernel<float><<<grid, 256, 0, s>>>(ia);
+    else if (dtype == KFAC_F16) im2col_kernel<__half><<<grid, 256, 0, s>>>(ia);
+    else if (dtype == KFAC_BF16) im2col_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(ia);
+    else { set_error("unknown dtype %d", dtype); return KFAC_ERR_BAD_ARG; }
+    KFAC_LAUNCH_CHECK();
+    CovArgs a{};
+    a.x = ws; a.ld = ld; a.batch_stride = 0; a.rows = (int)rows; a.batch = 1; a.feat = C; a.ones = 0;
+    a.scale = scale; a.acc = acc;
+    return launch_cov<true>(a, KFAC_F32, s);
+  }
   CovArgs a{};
   a.x = g; a.ld = (int64_t)Ho * Wo; a.batch_stride = (int64_t)C * Ho * Wo;
   a.rows = Ho * Wo; a.batch = batch; a.feat = C; a.ones = 0; a.scale = scale; a.acc = acc;

@@ -283,29 +283,30 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         }
         sub_sync(sg);
         const int tx = st_tid & 15, ty = st_tid >> 4;
-        float acc[4][4];
+        float2 acc[4][2];                              // 4 x 4 outputs as packed pairs (FFMA2)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
 #pragma unroll 8
         for (int k = 0; k < NB; ++k) {
           const float4 a1 = *reinterpret_cast<const float4*>(&VIt[k * UPAD + ty * 4]);
           const float4 b1 = *reinterpret_cast<const float4*>(&WJt[k * UPAD + tx * 4]);
           const float4 a2 = *reinterpret_cast<const float4*>(&WIt[k * UPAD + ty * 4]);
           const float4 b2 = *reinterpret_cast<const float4*>(&VJt[k * UPAD + tx * 4]);
-          const float av1[4] = {a1.x, a1.y, a1.z, a1.w}, bv1[4] = {b1.x, b1.y, b1.z, b1.w};
-          const float av2[4] = {a2.x, a2.y, a2.z, a2.w}, bv2[4] = {b2.x, b2.y, b2.z, b2.w};
+          const float av1[4] = {a1.x, a1.y, a1.z, a1.w}, av2[4] = {a2.x, a2.y, a2.z, a2.w};
+          const float2 b1lo = make_float2(b1.x, b1.y), b1hi = make_float2(b1.z, b1.w);
+          const float2 b2lo = make_float2(b2.x, b2.y), b2hi = make_float2(b2.z, b2.w);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av1[i], bv1[j], fmaf(av2[i], bv2[j], acc[i][j]));
+          for (int i = 0; i < 4; ++i) {
+            const float2 d1 = make_float2(av1[i], av1[i]), d2 = make_float2(av2[i], av2[i]);
+            acc[i][0] = fma2(d1, b1lo, fma2(d2, b2lo, acc[i][0]));
+            acc[i][1] = fma2(d1, b1hi, fma2(d2, b2hi, acc[i][1]));
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4* p = reinterpret_cast<float4*>(&mt.A[(int64_t)(I * T + ty * 4 + i) * np + J * T + tx * 4]);
           float4 a = __ldcg(p);
-          a.x -= acc[i][0]; a.y -= acc[i][1]; a.z -= acc[i][2]; a.w -= acc[i][3];
+          a.x -= acc[i][0].x; a.y -= acc[i][0].y; a.z -= acc[i][1].x; a.w -= acc[i][1].y;
           *p = a;
         }
       }

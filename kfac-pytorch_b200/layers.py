@@ -181,8 +181,12 @@ class Conv2dModuleHelper(ModuleHelper):
         S = Ho * Wo
         scale = 1.0 / (float(B) * float(S) ** 3 * grad_scale * grad_scale)
         lib = _cabi.load()
+        need = lib.kfac_factor_conv2d_gradout_workspace_bytes(B, Cc, Ho, Wo) if scratch is not None else 0
+        ws = scratch.get(need, g.device) if need else None
         _cabi.check(lib.kfac_factor_conv2d_gradout(g.data_ptr(), _dtype_code(g), B, Cc, Ho, Wo,
-                                                   scale, acc.data_ptr(), _cabi.stream_ptr()),
+                                                   scale, acc.data_ptr(),
+                                                   ws.data_ptr() if ws is not None else None, need,
+                                                   _cabi.stream_ptr()),
                     'kfac_factor_conv2d_gradout')
 
 

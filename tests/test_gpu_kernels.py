@@ -92,6 +92,8 @@ CONV_GEOS = [  # B, C, H, W, kh, kw, sh, sw, ph, pw, bias
     (4, 16, 9, 9, 2, 2, 1, 1, 0, 0, 1),     # reference modules_test geometry k2 s1 p0 bias
     (1, 5, 10, 6, 3, 2, 2, 1, 1, 0, 0),
     (8, 64, 14, 14, 3, 3, 1, 1, 1, 1, 0),
+    (8, 256, 7, 7, 1, 1, 1, 1, 0, 0, 0),    # 1x1 on 7x7 maps: rows of 49 floats are packed for the tensor-core SYRK
+    (4, 128, 7, 7, 1, 1, 1, 1, 0, 0, 1),
 ]
 
 
@@ -116,8 +118,10 @@ def test_factor_conv2d_input(lib, dev, geo):
     assert rel_fro(0.5 * (acc + acc.t()), ref) < 2e-5
 
 
-@pytest.mark.parametrize('B,Cc,Ho,Wo', [(2, 6, 8, 8), (3, 10, 3, 3), (4, 64, 14, 14), (2, 130, 5, 7), (1, 1, 1, 1)])
-def test_factor_conv2d_gradout(lib, dev, B, Cc, Ho, Wo):
+@pytest.mark.parametrize('B,Cc,Ho,Wo', [(2, 6, 8, 8), (3, 10, 3, 3), (4, 64, 14, 14), (2, 130, 5, 7), (1, 1, 1, 1),
+                                        (8, 256, 7, 7), (32, 512, 7, 7)])
+@pytest.mark.parametrize('with_ws', [True, False])
+def test_factor_conv2d_gradout(lib, dev, B, Cc, Ho, Wo, with_ws):
     from oracle import kfac_oracle as O
     torch.manual_seed(B + Cc)
     g = torch.randn(B, Cc, Ho, Wo)
@@ -125,7 +129,11 @@ def test_factor_conv2d_gradout(lib, dev, B, Cc, Ho, Wo):
     acc = torch.zeros(Cc, Cc, device=dev)
     gd = g.to(dev)
     scale = 1.0 / (B * float(Ho * Wo) ** 3)
-    assert lib.kfac_factor_conv2d_gradout(gd.data_ptr(), 0, B, Cc, Ho, Wo, scale, acc.data_ptr(), S()) == 0
+    need = lib.kfac_factor_conv2d_gradout_workspace_bytes(B, Cc, Ho, Wo) if with_ws else 0
+    assert (need > 0) == (with_ws and (Ho * Wo) % 4 != 0 and Cc >= 64)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    assert lib.kfac_factor_conv2d_gradout(gd.data_ptr(), 0, B, Cc, Ho, Wo, scale, acc.data_ptr(),
+                                          ws.data_ptr() if need else None, need, S()) == 0
     torch.cuda.synchronize()
     assert rel_fro(0.5 * (acc + acc.t()), ref) < 2e-5
 
