@@ -127,9 +127,10 @@ class PhaseTimer:
         self.pre = pre
         self.events = {}
         self.enabled = False
-        for name in ('_flush_factor_updates', '_reduce_factors', '_compute_inverses', '_precondition',
-                     '_scale_and_write_back'):
+        for name in ('_flush_factor_updates', '_compute_inverses', '_precondition', '_scale_and_write_back'):
             self._wrap(pre, name)
+        # C1 runs inside the flush (flush_factor_updates includes it); the A block is reduced under backward
+        self._wrap(pre, '_reduce_batches', 'reduce_factors')
         for _, layer in pre._layers.values():
             self._wrap(layer.module, 'accumulate_a', 'factor_a')
             self._wrap(layer.module, 'accumulate_g', 'factor_g')
@@ -192,7 +193,7 @@ def parity_step(pre, model, world, rank, dev, hp):
     """One UNTIMED step after the timed region, checked against the CPU oracle (test infrastructure used as
     the checker only; nothing here is timed or shipped).  ResNets hold BatchNorm, so the concatenated-batch
     equivalence of tests/dist_parity.py does not apply; instead:
-      C1   the all-reduced factor arena must equal the mean over ranks of the local (pre-reduce) arenas;
+      C1   the library's reduction of the batch-statistics arena must equal the mean over ranks of the local arenas;
       K5-K12 + C2 + C3   rank 0 recomputes, on the host with the oracle's operators, the preconditioned gradient
            of EVERY layer from the all-reduced factors and the DDP-averaged raw gradients, and compares it with
            the P this rank holds after step() (computed here or received from its KAISA source);
@@ -203,17 +204,19 @@ def parity_step(pre, model, world, rank, dev, hp):
     raw = [O.grad_matrix(l.module.get_weight_grad().detach().float().cpu(),
                          l.module.get_bias_grad().detach().float().cpu() if l.module.has_bias() else None)
            for l in layers] if rank == 0 else None
-    pre._flush_factor_updates()
     if world > 1:
-        local = pre._factor_arena.clone()
+        # the caller ran this step's forward/backward with pre.overlap_factor_allreduce = False: the batch statistics
+        # are still local here
+        local = pre._batch_arena.clone()
         dist.all_reduce(local)
         local /= world
+        pre._reduce_batches()
+        err = float((pre._batch_arena - local).norm() / local.norm())
+        out['factor_allreduce_rel_err'] = err
+        del local
     pre.step()
     torch.cuda.synchronize()
     if world > 1:
-        err = float((pre._factor_arena - local).norm() / local.norm())
-        out['factor_allreduce_rel_err'] = err
-        del local
         worst = torch.zeros(1, device=dev)
         for p in model.parameters():
             ref = p.grad.clone()
@@ -499,8 +502,10 @@ def run_b200(args):
         # one more (untimed) step on a fresh batch, checked against the CPU oracle
         x, y = devb[counter['i'] % NB]
         opt.zero_grad(set_to_none=True)
+        pre.overlap_factor_allreduce = False      # keep this step's statistics local until parity_step has cloned them
         crit(model(x), y).backward()
         out['parity'] = parity_step(pre, model, world, rank, dev, hp)
+        pre.overlap_factor_allreduce = True
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(args, steps=2, warmup=1, budget=150.0)
     if rank == 0:

@@ -208,8 +208,13 @@ class BaseKFACPreconditioner:
         self._eig_scratch = _Scratch()      # eigensolver workspace
         self._gemm_scratch = _Scratch()     # precondition / inverse temporaries
         self._grad_scratch = _Scratch()     # kl-clip / write-back item table + partial sums
-        self._factors_dirty = False
         self._pending_alpha: dict[float, list[tuple[KFACLayer, str]]] = {}
+        # C1: the batch statistics (not the factors) are averaged over the ranks BEFORE the EMA -- the same factors by
+        # linearity -- so that the A block can be reduced while backward still runs (base_preconditioner.py:452-457)
+        self.overlap_factor_allreduce = True
+        self._a_reduce_work: Any = None        # in-flight asynchronous all-reduce of the A block
+        self._a_block_reduced = False
+        self._comm_stream: torch.cuda.Stream | None = None
         self.last_grad_scale: torch.Tensor | None = None   # device scalar nu of the last step
         # store preconditioned gradients straight into the receivers' arenas (P2P) instead of broadcasting
         self.fused_grad_broadcast = True
@@ -275,13 +280,18 @@ class BaseKFACPreconditioner:
         total = sum(_cabi.ld4(l.a_dim ** 2) + _cabi.ld4(l.g_dim ** 2) for _, l in ll)
         self._factor_arena = torch.zeros(total, dtype=torch.float32, device=device)
         self._batch_arena = torch.zeros(total, dtype=torch.float32, device=device)
+        # layout: all A factors, then all G factors -- the A block is complete after the forward pass and is
+        # all-reduced on its own while backward produces the G statistics
         off = 0
-        for _, l in ll:
-            for dim, fa, ba in ((l.a_dim, '_a_view', '_a_batch_view'), (l.g_dim, '_g_view', '_g_batch_view')):
+        for which in ('a', 'g'):
+            for _, l in ll:
+                dim = l.a_dim if which == 'a' else l.g_dim
                 n = dim * dim
-                setattr(l, fa, self._factor_arena.narrow(0, off, n).view(dim, dim))
-                setattr(l, ba, self._batch_arena.narrow(0, off, n).view(dim, dim))
+                setattr(l, f'_{which}_view', self._factor_arena.narrow(0, off, n).view(dim, dim))
+                setattr(l, f'_{which}_batch_view', self._batch_arena.narrow(0, off, n).view(dim, dim))
                 off += _cabi.ld4(n)
+            if which == 'a':
+                self._a_block_numel = off
         # second-order data + preconditioned gradients
         self._inv_segments, self._grad_segments = build_comm_plan(ll, self._assignment)
         inv_total = sum(s.numel for s in self._inv_segments)
@@ -435,7 +445,6 @@ class BaseKFACPreconditioner:
             # snapshots (the arena views keep changing in place)
             if self._arenas_ready:
                 self._flush_factor_updates()
-                self._reduce_factors()
             sd['layers'] = {name: layer.state_dict() for name, layer in self._layers.values()}
         return sd
 
@@ -475,6 +484,12 @@ class BaseKFACPreconditioner:
         self._ensure_arenas(x.device)
         if layer._a_pending:       # a completed accumulation window is still queued
             self._flush_factor_updates()
+        if self._a_reduce_work is not None:
+            # another forward pass before step(): the overlapped reduction must not race with new statistics.
+            # What it averaged stays averaged; the flush reduces the block again (idempotent on the averaged part)
+            self._a_reduce_work.wait()
+            self._a_reduce_work = None
+            self._a_block_reduced = False
         layer.module.accumulate_a(cast_for_factor(x, layer.factor_dtype), layer._a_batch_view, self._scratch)
         layer._a_count += 1
         self._mini_steps[name] += 1
@@ -493,6 +508,8 @@ class BaseKFACPreconditioner:
         self._ensure_arenas(g.device)
         if layer._g_pending:
             self._flush_factor_updates()
+        if self._update_factors_in_hook and self._mini_steps[name] % self._accumulation_steps == 0:
+            self._launch_a_block_reduction()     # first backward hook of the window: every A statistic is complete
         # the backward hook runs on the autograd thread: it gets its own scratch buffer
         layer.module.accumulate_g(cast_for_factor(g, layer.factor_dtype), layer._g_batch_view,
                                   self._grad_scale_value(layer), self._scratch_bwd)
@@ -512,9 +529,70 @@ class BaseKFACPreconditioner:
             layer._g_pending = True
         self._pending_alpha.setdefault(float(self.factor_decay), []).append((layer, which))
 
+    def _launch_a_block_reduction(self) -> None:
+        """Asynchronous all-reduce (average) of the A block of the batch statistics on a side stream, launched from the
+        backward hook that fires first: it overlaps with the rest of backward (the reference launches its factor
+        all-reduces from the hooks for the same reason, base_preconditioner.py:452-457, layers/base.py:282-336)."""
+        import torch.distributed as dist
+        from kfac_b200.distributed import get_world_size
+        if (not self.overlap_factor_allreduce or self._a_reduce_work is not None or self._a_block_reduced
+                or get_world_size() == 1 or dist.get_backend() != 'nccl'):
+            return
+        ll = self._layer_list()
+        if not ll or ll[0][1].symmetry_aware:       # packed triangles are reduced in one piece at the flush
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self._device)
+        done = torch.cuda.current_stream(self._device).record_event()
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(done)
+            self._a_reduce_work = dist.all_reduce(self._batch_arena.narrow(0, 0, self._a_block_numel),
+                                                  op=dist.ReduceOp.AVG, async_op=True)
+        self._tdc.calls['allreduce'] += 1
+
+    def _reduce_batches(self) -> None:
+        """C1: average the pending batch statistics over all ranks (whatever the hooks have not reduced yet).
+        Averaging a block twice is harmless (the second average of identical values is the identity)."""
+        from kfac_b200.distributed import get_world_size
+        if get_world_size() == 1:
+            return
+        if self._a_reduce_work is not None:
+            self._a_reduce_work.wait()            # the current stream waits for the collective; the host does not
+            self._a_reduce_work = None
+            self._a_block_reduced = True
+        ll = self._layer_list()
+        if ll and ll[0][1].symmetry_aware:
+            # communicate only the upper triangles (kfac/distributed.py:422-465):
+            # pack -> one all-reduce of the packed arena -> mirror back
+            lib = _cabi.load()
+            stream = _cabi.stream_ptr()
+            if getattr(self, '_packed_arena', None) is None:
+                total = sum(l.a_dim * (l.a_dim + 1) // 2 + l.g_dim * (l.g_dim + 1) // 2 for _, l in ll)
+                self._packed_arena = torch.empty(total, dtype=torch.float32, device=self._device)
+            off = 0
+            todo = []
+            for _, l in ll:
+                for view, d in ((l._a_batch_view, l.a_dim), (l._g_batch_view, l.g_dim)):
+                    n = d * (d + 1) // 2
+                    todo.append((view, d, self._packed_arena.narrow(0, off, n)))
+                    off += n
+            for view, d, packed in todo:
+                _cabi.check(lib.kfac_triu_pack(view.data_ptr(), d, packed.data_ptr(), stream), 'kfac_triu_pack')
+            self._tdc.allreduce_average(self._packed_arena, group=None)
+            for view, d, packed in todo:
+                _cabi.check(lib.kfac_triu_unpack(packed.data_ptr(), d, view.data_ptr(), stream), 'kfac_triu_unpack')
+        elif self._a_block_reduced:
+            total = self._batch_arena.numel()
+            self._tdc.allreduce_average(self._batch_arena.narrow(0, self._a_block_numel, total - self._a_block_numel),
+                                        group=None)
+        else:
+            self._tdc.allreduce_average(self._batch_arena, group=None)
+        self._a_block_reduced = False
+
     def _flush_factor_updates(self) -> None:
         if not self._pending_alpha:
             return
+        self._reduce_batches()
         lib = _cabi.load()
         for alpha, todo in self._pending_alpha.items():
             items = (_cabi.EmaItem * len(todo))()
@@ -529,7 +607,6 @@ class BaseKFACPreconditioner:
                     layer._has_g, layer._g_count, layer._g_pending = True, 0, False
             _cabi.check(lib.kfac_factor_ema(items, len(todo), alpha, _cabi.stream_ptr()), 'kfac_factor_ema')
         self._pending_alpha = {}
-        self._factors_dirty = True
 
     # ------------------------------------------------------------ step
     @torch.no_grad()
@@ -545,8 +622,7 @@ class BaseKFACPreconditioner:
                 self._mini_steps[name] = 0
                 self._mark_pending(layer, 'a')
                 self._mark_pending(layer, 'g')
-        self._flush_factor_updates()
-        self._reduce_factors()
+        self._flush_factor_updates()      # C1 (average of the batch statistics) + EMA
 
         if self.steps % self.inv_update_steps == 0:
             self._compute_inverses()
@@ -556,38 +632,6 @@ class BaseKFACPreconditioner:
 
         self._steps += 1
         self._mini_steps = defaultdict(int)
-
-    # C1 -----------------------------------------------------------------
-    def _reduce_factors(self) -> None:
-        if not self._factors_dirty:
-            return
-        self._factors_dirty = False
-        from kfac_b200.distributed import get_world_size
-        if get_world_size() == 1:
-            return
-        ll = self._layer_list()
-        if ll and ll[0][1].symmetry_aware:
-            # communicate only the upper triangles (kfac/distributed.py:422-465):
-            # pack -> one all-reduce of the packed arena -> mirror back
-            lib = _cabi.load()
-            stream = _cabi.stream_ptr()
-            if getattr(self, '_packed_arena', None) is None:
-                total = sum(l.a_dim * (l.a_dim + 1) // 2 + l.g_dim * (l.g_dim + 1) // 2 for _, l in ll)
-                self._packed_arena = torch.empty(total, dtype=torch.float32, device=self._device)
-            off = 0
-            todo = []
-            for _, l in ll:
-                for view, d in ((l._a_view, l.a_dim), (l._g_view, l.g_dim)):
-                    n = d * (d + 1) // 2
-                    todo.append((view, d, self._packed_arena.narrow(0, off, n)))
-                    off += n
-            for view, d, packed in todo:
-                _cabi.check(lib.kfac_triu_pack(view.data_ptr(), d, packed.data_ptr(), stream), 'kfac_triu_pack')
-            self._tdc.allreduce_average(self._packed_arena, group=None)
-            for view, d, packed in todo:
-                _cabi.check(lib.kfac_triu_unpack(packed.data_ptr(), d, view.data_ptr(), stream), 'kfac_triu_unpack')
-            return
-        self._tdc.allreduce_average(self._factor_arena, group=None)
 
     def _check_eigh_status(self, wait: bool) -> None:
         """Raise if the last eigendecomposition reported non-convergence or non-finite eigenvalues

@@ -84,6 +84,12 @@ def main():
                 print(f'world={world} method={method} symmetry_aware={sym} grad_worker_fraction={frac:.3f} '
                       f'collectives={pre._tdc.calls} worst rel-fro vs oracle = {t.item():.2e}', flush=True)
             ok = ok and t.item() < 1e-3
+            # C1: the A block of the batch statistics is all-reduced from the first backward hook (overlapped with
+            # backward), the G block at step(); packed triangles (symmetry_aware) go in one piece at step()
+            want_calls = 3 * (1 if sym else 2)
+            if pre._tdc.calls['allreduce'] != want_calls:
+                print(f'rank {rank}: {pre._tdc.calls["allreduce"]} factor all-reduces, expected {want_calls}', flush=True)
+                ok = False
     # wide layers (a = 833 / 769, g = 768): the large-matrix eigensolver class, an eigenbasis broadcast
     # segment of several MB (C2) and a multi-tile (6 x 7 tiles of 128 x 128) tcgen05 precondition epilogue
     # that stores straight into the peers' arenas (fused compute + broadcast, C3)
@@ -97,7 +103,7 @@ def main():
         def forward(self, x):
             return self.l3(torch.tanh(self.l2(torch.tanh(self.l1(x)))))
 
-    for frac in sorted({1.0 / world, 0.5 if world % 2 == 0 else 1.0 / world}):
+    for wi, frac in enumerate(sorted({1.0 / world, 0.5 if world % 2 == 0 else 1.0 / world})):
         torch.manual_seed(0)
         ref_model = Wide()
         model = copy.deepcopy(ref_model).to(dev)
@@ -106,6 +112,7 @@ def main():
         gy = torch.randint(0, 5, (world * 16,))
         x, y = gx[rank * 16:(rank + 1) * 16].to(dev), gy[rank * 16:(rank + 1) * 16].to(dev)
         pre = KFACPreconditioner(model, damping=0.003, grad_worker_fraction=frac)
+        pre.overlap_factor_allreduce = wi != 0       # the first configuration takes the one-piece reduction at step()
         ref = OraclePreconditioner(ref_model, damping=0.003) if rank == 0 else None
         worst = 0.0
         for step in range(2):
@@ -129,7 +136,7 @@ def main():
         t = torch.tensor([worst], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f'world={world} wide-MLP grad_worker_fraction={frac:.3f} fused={pre._peer_p_bases is not None} '
+            print(f'world={world} wide-MLP grad_worker_fraction={frac:.3f} overlap={pre.overlap_factor_allreduce} fused={pre._peer_p_bases is not None} '
                   f'collectives={pre._tdc.calls} worst rel-fro vs oracle = {t.item():.2e}', flush=True)
         ok = ok and t.item() < 1e-3
     dist.barrier()
