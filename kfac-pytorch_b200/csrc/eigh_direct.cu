@@ -14,25 +14,30 @@ namespace kfac {
 
 namespace {
 
-constexpr int BT = 128;     // Householder vectors per block reflector of the back-transformation
+constexpr int BT = TRD_BT;  // Householder vectors per block reflector of the back-transformation
+constexpr int LB = 128;     // T factors are built for LB-wide halves and merged: T = [T1, -T1 (V1^T V2) T2; 0, T2]
+static_assert(BT == 2 * LB, "block reflectors are merged from two halves");
 
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
-struct BtBlock { float* S; float* Tm; const float* tau; int nb; };
+struct BtBlock { float* S; float* Tm; float* TmT; const float* tau; int nb; };
 
-// S = V^T V of one block -> T (upper triangular, forward columnwise: H_0 H_1 ... = I - V T V^T)
-__global__ void __launch_bounds__(BT) larft_kernel(const BtBlock* blocks) {
+// S = V^T V of one block -> T (upper triangular, forward columnwise: H_0 H_1 ... = I - V T V^T) of its two LB-wide halves
+// (CTA 2 b + h: half h of block b); the off-diagonal quadrant follows from two small GEMMs (eigh_direct_run).
+// TmT receives the transposes of the diagonal quadrants (operands of those GEMMs).
+__global__ void __launch_bounds__(LB) larft_kernel(const BtBlock* blocks) {
   extern __shared__ float larft_smem[];
-  float (*Ts)[BT + 1] = reinterpret_cast<float (*)[BT + 1]>(larft_smem);
-  const BtBlock b = blocks[blockIdx.x];
-  const int i = threadIdx.x, nb = b.nb;
-  for (int j = 0; j < BT; ++j) Ts[i][j] = 0.f;
+  float (*Ts)[LB + 1] = reinterpret_cast<float (*)[LB + 1]>(larft_smem);
+  const BtBlock b = blocks[blockIdx.x >> 1];
+  const int o = (blockIdx.x & 1) * LB;
+  const int i = threadIdx.x, nb = max(0, min(LB, b.nb - o));
+  for (int j = 0; j < LB; ++j) Ts[i][j] = 0.f;
   __syncthreads();
   for (int j = 0; j < nb; ++j) {
-    const float tj = b.tau[j];
+    const float tj = b.tau[o + j];
     float acc = 0.f;
     if (i < j) {
-      for (int l = i; l < j; ++l) acc = fmaf(Ts[i][l], b.S[l * BT + j], acc);
+      for (int l = i; l < j; ++l) acc = fmaf(Ts[i][l], b.S[(o + l) * BT + o + j], acc);
       acc *= -tj;
     }
     __syncthreads();
@@ -40,7 +45,10 @@ __global__ void __launch_bounds__(BT) larft_kernel(const BtBlock* blocks) {
     if (i == j) Ts[i][j] = tj;
     __syncthreads();
   }
-  for (int j = 0; j < BT; ++j) b.Tm[i * BT + j] = Ts[i][j];
+  for (int j = 0; j < LB; ++j) {
+    b.Tm[(o + j) * BT + o + i] = Ts[j][i];       // row j, coalesced over i
+    b.TmT[(o + j) * BT + o + i] = Ts[i][j];
+  }
 }
 
 // A (np x np, zero padded) <- F (n x n, ld n).  Entries that are not finite, or so large that the squared column norms of
@@ -91,7 +99,7 @@ __global__ void clamp_copy_kernel(const float* src, float* dst, int n, int* stat
 
 struct MatLayout {
   int n, np, nblk, nbt;
-  size_t A, VT, Vb, Q0, Q1, P, Vp, Wp, part, col, tau, d, e, cpart, bar, fscr, iscr, S, Tm, Y, Y2, slabY, slabS;
+  size_t A, VT, Vb, Q0, Q1, P, Vp, Wp, part, col, tau, d, e, cpart, bar, fscr, iscr, S, Tm, TmT, Xt, Y, Y2, slabY, slabS;
   int ksplit;      // split count of the longest reduction of the back-transformation (K = np)
 };
 
@@ -131,7 +139,8 @@ void make_layout(const int* n, int count, Layout& L) {
     m.cpart = take((size_t)grid * TRD_CP * 4);
     m.bar = take(256);
     m.fscr = take((size_t)12 * m.n * 4); m.iscr = take((size_t)12 * m.n * 4);
-    m.S = take((size_t)m.nbt * BT * BT * 4); m.Tm = take((size_t)m.nbt * BT * BT * 4);
+    m.S = take((size_t)m.nbt * BT * BT * 4); m.Tm = take((size_t)m.nbt * BT * BT * 4); m.TmT = take((size_t)m.nbt * BT * BT * 4);
+    m.Xt = take((size_t)m.nbt * LB * LB * 4);
   }
   L.total = off;
 }
@@ -299,8 +308,12 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     for (int kb = 0; kb < m.nbt; ++kb) {
       const int j0 = kb * BT, nb = std::min(BT, m.n - j0);
       blocks.push_back(BtBlock{(float*)(base + m.S) + (size_t)kb * BT * BT, (float*)(base + m.Tm) + (size_t)kb * BT * BT,
-                               trd[i].tau + j0, nb});
+                               (float*)(base + m.TmT) + (size_t)kb * BT * BT, trd[i].tau + j0, nb});
     }
+    // S beyond the valid reflectors and the off-diagonal quadrants of T must be zero
+    KFAC_CUDA(cudaMemsetAsync(base + m.S, 0, (size_t)m.nbt * BT * BT * 4, s));
+    KFAC_CUDA(cudaMemsetAsync(base + m.Tm, 0, (size_t)m.nbt * BT * BT * 4, s));
+    KFAC_CUDA(cudaMemsetAsync(base + m.TmT, 0, (size_t)m.nbt * BT * BT * 4, s));
   }
   BtBlock* d_blocks = (BtBlock*)(base + L.off_blocks);
   KFAC_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(BtBlock) * blocks.size(), cudaMemcpyHostToDevice, s));
@@ -332,10 +345,31 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
   }
   {
     static bool attr = false;
-    const int lsmem = BT * (BT + 1) * (int)sizeof(float);
+    const int lsmem = LB * (LB + 1) * (int)sizeof(float);
     if (!attr) { KFAC_CUDA(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lsmem)); attr = true; }
-    larft_kernel<<<(int)blocks.size(), BT, lsmem, s>>>(d_blocks);
+    larft_kernel<<<2 * (int)blocks.size(), LB, lsmem, s>>>(d_blocks);
     KFAC_LAUNCH_CHECK();
+    // T12 = -T1 (S12 T2) for every block with more than LB reflectors: X^T = T2^T S12^T, then T12 = -T1 X
+    std::vector<GroupedGemm> x1, x2;
+    for (int i = 0; i < count; ++i) {
+      const MatLayout& m = L.m[i];
+      for (int kb = 0; kb < m.nbt; ++kb) {
+        const int nb = std::min(BT, m.n - kb * BT);
+        if (nb <= LB) continue;
+        float* S = (float*)(base + m.S) + (size_t)kb * BT * BT;
+        float* Tm = (float*)(base + m.Tm) + (size_t)kb * BT * BT;
+        float* TmT = (float*)(base + m.TmT) + (size_t)kb * BT * BT;
+        float* Xt = (float*)(base + m.Xt) + (size_t)kb * LB * LB;
+        x1.push_back(plain(TmT + (size_t)LB * BT + LB, BT, S + LB, BT, Xt, LB, LB, LB, LB));
+        GroupedGemm g = plain(Tm, BT, Xt, LB, Tm + LB, BT, LB, LB, LB);
+        g.alpha = -1.f;
+        x2.push_back(g);
+      }
+    }
+    if (!x1.empty()) {
+      if ((rc = launch_grouped_gemm(x1.data(), (int)x1.size(), gws, L.gws_bytes, s))) return rc;
+      if ((rc = launch_grouped_gemm(x2.data(), (int)x2.size(), gws, L.gws_bytes, s))) return rc;
+    }
   }
   int max_nbt = 0;
   for (int i = 0; i < count; ++i) {

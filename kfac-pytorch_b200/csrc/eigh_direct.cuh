@@ -14,7 +14,7 @@ namespace kfac {
 constexpr int TRD_NB = 32;        // panel width (columns per block reflector of the reduction)
 constexpr int TRD_T = 64;         // tile edge of the lower-triangle tiling
 constexpr int TRD_THREADS = 1024; // 4 sub-groups of 8 warps
-constexpr int TRD_BT = 128;       // Householder vectors per block reflector of the back-transformation
+constexpr int TRD_BT = 256;       // Householder vectors per block reflector of the back-transformation
 constexpr int TRD_CP = 72;        // floats of per-CTA partial scalars: [0,32) W^T v, [32,64) V^T v, 64 v^T A v, 65 |x|^2
 
 struct TrdMat {
