@@ -51,49 +51,84 @@ __global__ void __launch_bounds__(LB) larft_kernel(const BtBlock* blocks) {
   }
 }
 
-// A (np x np, zero padded) <- F (n x n, ld n).  Entries that are not finite, or so large that the squared column norms of
-// the reduction could overflow (|x| > 1e15), are replaced by 0 and reported in the status word (bit 1): the solve then
-// runs on finite data (no NaN reaches the index arithmetic of the divide and conquer) and the caller sees the failure.
-__global__ void pad_copy_kernel(const float* F, int n, float* A, int np, int* status) {
+// per-matrix pointers of the batched input / output kernels (one launch over all matrices of the call)
+struct IoMat {
+  const float* F; float* A;              // input factor (n x n, ld n) -> zero-padded working copy (np x np)
+  const float* Z; float* ZT;             // eigenvectors of T (columns) -> their transpose, both np-strided
+  float* Q; float* QT; int ldq;          // user outputs
+  const float* dsrc; float* ddst;        // eigenvalues
+  int n, np;
+};
+
+// A (np x np, zero padded) <- F (n x n, ld n), grid (x, matrix).  Entries that are not finite, or so large that the squared
+// column norms of the reduction could overflow (|x| > 1e15), are replaced by 0 and reported in the status word (bit 1):
+// the solve then runs on finite data (no NaN reaches the index arithmetic of the divide and conquer) and the caller
+// sees the failure.
+__global__ void pad_copy_kernel(const IoMat* mats, int* status) {
+  const IoMat mt = mats[blockIdx.y];
+  const int n = mt.n, np = mt.np;
   const int64_t total = (int64_t)np * np;
   bool bad = false;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx / np), j = (int)(idx % np);
-    float x = (i < n && j < n) ? F[(int64_t)i * n + j] : 0.f;
+    float x = (i < n && j < n) ? mt.F[(int64_t)i * n + j] : 0.f;
     if (!(fabsf(x) <= 1e15f)) { bad = true; x = 0.f; }
-    A[idx] = x;
+    mt.A[idx] = x;
   }
   if (bad && status) atomicOr(status, 2);
 }
 
-__global__ void transpose_ld_kernel(const float* src, int lds, float* dst, int ldd, int rows, int cols) {
+// ZT = Z^T for every matrix: grid (tiles, tiles, matrix)
+__global__ void transpose_z_kernel(const IoMat* mats) {
   __shared__ float tile[32][33];
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const IoMat mt = mats[blockIdx.z];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32, n = mt.n;
+  if (bx >= n || by >= n) return;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int i = by + r, j = bx + threadIdx.x;
-    tile[r][threadIdx.x] = (i < rows && j < cols) ? src[(int64_t)i * lds + j] : 0.f;
+    tile[r][threadIdx.x] = (i < n && j < n) ? mt.Z[(int64_t)i * mt.np + j] : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int j = bx + r, i = by + threadIdx.x;
-    if (j < cols && i < rows) dst[(int64_t)j * ldd + i] = tile[threadIdx.x][r];
+    if (j < n && i < n) mt.ZT[(int64_t)j * mt.np + i] = tile[threadIdx.x][r];
   }
 }
 
-// final outputs: QT_user / Q_user from ZT (rows = eigenvectors), eigenvalues clamped at 0 (eigen.py:321,344)
-__global__ void copy_rows_kernel(const float* src, int lds, float* dst, int ldd, int rows, int cols) {
-  const int64_t total = (int64_t)rows * cols;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(idx / cols), j = (int)(idx % cols);
-    dst[(int64_t)i * ldd + j] = src[(int64_t)i * lds + j];
+// final outputs of every matrix from ZT (rows = eigenvectors): QT_user = ZT, Q_user = ZT^T (one read of the tile),
+// eigenvalues clamped at 0 (eigen.py:321,344); grid (tiles, tiles, matrix)
+__global__ void outputs_kernel(const IoMat* mats, int* status) {
+  __shared__ float tile[32][33];
+  const IoMat mt = mats[blockIdx.z];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32, n = mt.n;
+  if (bx >= n || by >= n) return;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = by + r, j = bx + threadIdx.x;
+    const float v = (i < n && j < n) ? mt.ZT[(int64_t)i * mt.np + j] : 0.f;
+    tile[r][threadIdx.x] = v;
+    if (mt.QT && i < n && j < n) mt.QT[(int64_t)i * mt.ldq + j] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int j = bx + r, i = by + threadIdx.x;
+    if (j < n && i < n) mt.Q[(int64_t)j * mt.ldq + i] = tile[threadIdx.x][r];
+  }
+  if (blockIdx.y == 0 && threadIdx.y == 0) {
+    const int j = bx + threadIdx.x;
+    if (j < n) {
+      const float v = mt.dsrc[j];
+      if (!isfinite(v) && status) atomicOr(status, 2);
+      mt.ddst[j] = fmaxf(v, 0.f);
+    }
   }
 }
-__global__ void clamp_copy_kernel(const float* src, float* dst, int n, int* status) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const float v = src[i];
-    if (!isfinite(v) && status) atomicOr(status, 2);
-    dst[i] = fmaxf(v, 0.f);
+
+// single-matrix helpers of the test entries
+__global__ void pad_copy_one_kernel(const float* F, int n, float* A, int np) {
+  const int64_t total = (int64_t)np * np;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / np), j = (int)(idx % np);
+    A[idx] = (i < n && j < n) ? F[(int64_t)i * n + j] : 0.f;
   }
 }
 
@@ -105,7 +140,7 @@ struct MatLayout {
 
 struct Layout {
   std::vector<MatLayout> m;
-  size_t off_trd, off_jobs, off_dc, off_blocks, off_plan, plan_bytes, off_gws, gws_bytes, total;
+  size_t off_trd, off_jobs, off_dc, off_blocks, off_io, off_plan, plan_bytes, off_gws, gws_bytes, zero_begin, zero_end, total;
   int nblocks;
 };
 
@@ -119,27 +154,38 @@ void make_layout(const int* n, int count, Layout& L) {
   L.nblocks = 0;
   for (int i = 0; i < count; ++i) L.nblocks += ceil_div(n[i], BT);
   L.off_blocks = take(sizeof(BtBlock) * std::max(1, L.nblocks));
+  L.off_io = take(sizeof(IoMat) * count);
   L.plan_bytes = stedc_plan_bytes(n, count);
   L.off_plan = take(L.plan_bytes);
   L.gws_bytes = grouped_gemm_ws_bytes(std::max(L.nblocks, count));
   L.off_gws = take(L.gws_bytes);
   const int grid = sytrd_max_grid();
+  // everything that must start as zeros lies in ONE region (one memset per call): the reflector stores (their padding
+  // is a GEMM reduction dimension), the panel, barrier and partial-scalar state of the tridiagonalisation, the two
+  // eigenvector buffers of the divide and conquer (off-diagonal blocks), S and the T factors
+  L.zero_begin = off;
   for (int i = 0; i < count; ++i) {
     MatLayout& m = L.m[i];
     m.n = n[i]; m.np = round_up(n[i], TRD_T); m.nblk = m.np / TRD_T; m.nbt = ceil_div(n[i], BT);
-    const size_t sq = (size_t)m.np * m.np * sizeof(float);
-    m.A = take(sq + (size_t)m.np * BT * 4); m.VT = take(sq); m.Vb = take(sq + (size_t)m.np * BT * 4); m.Q0 = take(sq); m.Q1 = take(sq); m.P = take(sq);
     m.ksplit = m.np > 1024 ? ceil_div(m.np, 512) : 1;
+    const size_t sq = (size_t)m.np * m.np * sizeof(float);
+    m.VT = take(sq); m.Vb = take(sq + (size_t)m.np * BT * 4); m.Q0 = take(sq); m.Q1 = take(sq);
+    m.Vp = take((size_t)m.np * TRD_NB * 4); m.Wp = take((size_t)m.np * TRD_NB * 4);
+    m.cpart = take((size_t)grid * TRD_CP * 4);
+    m.bar = take(256);
+    m.S = take((size_t)m.nbt * BT * BT * 4); m.Tm = take((size_t)m.nbt * BT * BT * 4); m.TmT = take((size_t)m.nbt * BT * BT * 4);
+  }
+  L.zero_end = off;
+  for (int i = 0; i < count; ++i) {
+    MatLayout& m = L.m[i];
+    const size_t sq = (size_t)m.np * m.np * sizeof(float);
+    m.A = take(sq + (size_t)m.np * BT * 4); m.P = take(sq);
     m.Y = take((size_t)m.np * BT * 4); m.Y2 = take((size_t)m.np * BT * 4);
     m.slabY = take((size_t)m.ksplit * m.np * BT * 4);
     m.slabS = take((size_t)m.nbt * m.ksplit * BT * BT * 4);
-    m.Vp = take((size_t)m.np * TRD_NB * 4); m.Wp = take((size_t)m.np * TRD_NB * 4);
     m.part = take((size_t)m.nblk * m.np * 4);
     m.col = take((size_t)m.np * 4); m.tau = take((size_t)m.np * 4); m.d = take((size_t)m.np * 4); m.e = take((size_t)m.np * 4);
-    m.cpart = take((size_t)grid * TRD_CP * 4);
-    m.bar = take(256);
     m.fscr = take((size_t)12 * m.n * 4); m.iscr = take((size_t)12 * m.n * 4);
-    m.S = take((size_t)m.nbt * BT * BT * 4); m.Tm = take((size_t)m.nbt * BT * BT * 4); m.TmT = take((size_t)m.nbt * BT * BT * 4);
     m.Xt = take((size_t)m.nbt * LB * LB * 4);
   }
   L.total = off;
@@ -279,16 +325,22 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     d.P = (float*)(base + m.P);
     d.fscr = (float*)(base + m.fscr); d.iscr = (int*)(base + m.iscr);
     d.n = m.n; d.ld = m.np; d.result_buf = 0;
-    // inputs / zeroed state
-    pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)m.np * m.np, 256)), 256, 0, s>>>(items[i].F, m.n, t.A, m.np, status);
-    KFAC_LAUNCH_CHECK();
-    KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)m.np * m.np * 4, s));
-    KFAC_CUDA(cudaMemsetAsync(t.Vb, 0, (size_t)m.np * (m.np + BT) * 4, s));
-    KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)m.np * TRD_NB * 4, s));
-    KFAC_CUDA(cudaMemsetAsync(t.Wp, 0, (size_t)m.np * TRD_NB * 4, s));
-    KFAC_CUDA(cudaMemsetAsync(t.bar, 0, 256, s));
-    KFAC_CUDA(cudaMemsetAsync(t.cpart, 0, (size_t)G * TRD_CP * 4, s));     // (epoch, value) slots: epoch 0 = nothing published
   }
+  // inputs / zeroed state: one memset, one padding launch
+  KFAC_CUDA(cudaMemsetAsync(base + L.zero_begin, 0, L.zero_end - L.zero_begin, s));
+  std::vector<IoMat> io(count);
+  for (int i = 0; i < count; ++i) {
+    const MatLayout& m = L.m[i];
+    IoMat& o = io[i];
+    o.F = items[i].F; o.A = trd[i].A; o.n = m.n; o.np = m.np;
+    o.Q = items[i].Q; o.QT = items[i].QT; o.ldq = items[i].ldq > 0 ? items[i].ldq : m.n;
+    o.dsrc = trd[i].d; o.ddst = items[i].d;
+    o.Z = nullptr; o.ZT = nullptr;
+  }
+  IoMat* d_io = (IoMat*)(base + L.off_io);
+  KFAC_CUDA(cudaMemcpyAsync(d_io, io.data(), sizeof(IoMat) * count, cudaMemcpyHostToDevice, s));
+  pad_copy_kernel<<<dim3(std::min(1024, ceil_div((int64_t)np_max * np_max, 256)), count), 256, 0, s>>>(d_io, status);
+  KFAC_LAUNCH_CHECK();
   std::vector<TrdJob> jobs;
   make_schedule(ns.data(), count, G, jobs);
   TrdMat* d_trd = (TrdMat*)(base + L.off_trd);
@@ -299,7 +351,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
   KFAC_CUDA(cudaMemcpyAsync(d_dc, dc.data(), sizeof(DcMat) * count, cudaMemcpyHostToDevice, s));
   int rc;
   if ((rc = launch_sytrd(d_trd, d_jobs, (int)jobs.size(), np_max, G, s))) return rc;
-  if ((rc = launch_stedc(dc.data(), d_dc, count, base + L.off_plan, L.plan_bytes, status, s))) return rc;
+  if ((rc = launch_stedc(dc.data(), d_dc, count, base + L.off_plan, L.plan_bytes, status, s, /*q_zeroed=*/true))) return rc;
 
   // ---- back-transformation: QT = Z^T B_{L-1}^T ... B_0^T, B_k = I - V_k T_k V_k^T
   std::vector<BtBlock> blocks;
@@ -310,10 +362,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
       blocks.push_back(BtBlock{(float*)(base + m.S) + (size_t)kb * BT * BT, (float*)(base + m.Tm) + (size_t)kb * BT * BT,
                                (float*)(base + m.TmT) + (size_t)kb * BT * BT, trd[i].tau + j0, nb});
     }
-    // S beyond the valid reflectors and the off-diagonal quadrants of T must be zero
-    KFAC_CUDA(cudaMemsetAsync(base + m.S, 0, (size_t)m.nbt * BT * BT * 4, s));
-    KFAC_CUDA(cudaMemsetAsync(base + m.Tm, 0, (size_t)m.nbt * BT * BT * 4, s));
-    KFAC_CUDA(cudaMemsetAsync(base + m.TmT, 0, (size_t)m.nbt * BT * BT * 4, s));
+    // (S beyond the valid reflectors and the off-diagonal quadrants of T are zero: part of the zeroed region)
   }
   BtBlock* d_blocks = (BtBlock*)(base + L.off_blocks);
   KFAC_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(BtBlock) * blocks.size(), cudaMemcpyHostToDevice, s));
@@ -371,15 +420,18 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
       if ((rc = launch_grouped_gemm(x2.data(), (int)x2.size(), gws, L.gws_bytes, s))) return rc;
     }
   }
-  int max_nbt = 0;
+  int max_nbt = 0, n_max = 0;
   for (int i = 0; i < count; ++i) {
     const MatLayout& m = L.m[i];
     const DcMat& d = dc[i];
     max_nbt = std::max(max_nbt, m.nbt);
-    transpose_ld_kernel<<<dim3(ceil_div(m.n, 32), ceil_div(m.n, 32)), dim3(32, 8), 0, s>>>(d.Q[d.result_buf], m.np,
-                                                                                          d.Q[d.result_buf ^ 1], m.np, m.n, m.n);
-    KFAC_LAUNCH_CHECK();
+    n_max = std::max(n_max, m.n);
+    io[i].Z = d.Q[d.result_buf]; io[i].ZT = d.Q[d.result_buf ^ 1];
   }
+  // (the table is re-sent with the buffer parity the plan of the divide and conquer ended on)
+  KFAC_CUDA(cudaMemcpyAsync(d_io, io.data(), sizeof(IoMat) * count, cudaMemcpyHostToDevice, s));
+  transpose_z_kernel<<<dim3(ceil_div(n_max, 32), ceil_div(n_max, 32), count), dim3(32, 8), 0, s>>>(d_io);
+  KFAC_LAUNCH_CHECK();
   // block reflectors, last block first; step t handles block (nbt - 1 - t) of every matrix that still has one:
   // three grouped launches per step instead of three GEMMs per block and matrix
   for (int tstep = 0; tstep < max_nbt; ++tstep) {
@@ -408,21 +460,8 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
     if ((rc = launch_grouped_gemm(g2.data(), (int)g2.size(), gws, L.gws_bytes, s))) return rc;
     if ((rc = launch_grouped_gemm(g3.data(), (int)g3.size(), gws, L.gws_bytes, s))) return rc;
   }
-  for (int i = 0; i < count; ++i) {
-    const MatLayout& m = L.m[i];
-    const DcMat& d = dc[i];
-    const int n = m.n, np = m.np;
-    const float* ZT = d.Q[d.result_buf ^ 1];
-    const int ldq = items[i].ldq > 0 ? items[i].ldq : n;
-    if (items[i].QT) {
-      copy_rows_kernel<<<std::min(2048, ceil_div((int64_t)n * n, 256)), 256, 0, s>>>(ZT, np, items[i].QT, ldq, n, n);
-      KFAC_LAUNCH_CHECK();
-    }
-    transpose_ld_kernel<<<dim3(ceil_div(n, 32), ceil_div(n, 32)), dim3(32, 8), 0, s>>>(ZT, np, items[i].Q, ldq, n, n);
-    KFAC_LAUNCH_CHECK();
-    clamp_copy_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d.d, items[i].d, n, status);
-    KFAC_LAUNCH_CHECK();
-  }
+  outputs_kernel<<<dim3(ceil_div(n_max, 32), ceil_div(n_max, 32), count), dim3(32, 8), 0, s>>>(d_io, status);
+  KFAC_LAUNCH_CHECK();
   return KFAC_OK;
 }
 
@@ -450,7 +489,7 @@ extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e
   t.e = (float*)(base + oE); t.Vp = (float*)(base + oVp); t.Wp = (float*)(base + oWp); t.part = (float*)(base + oPart);
   t.col = (float*)(base + oCol); t.cpart = (float*)(base + oC); t.bar = (unsigned int*)(base + oBar);
   t.n = n; t.np = np; t.nblk = nblk; t.ldv = np; t.Vb = nullptr;
-  pad_copy_kernel<<<std::min(1024, ceil_div((int64_t)np * np, 256)), 256, 0, s>>>(F, n, t.A, np, nullptr);
+  pad_copy_one_kernel<<<std::min(1024, ceil_div((int64_t)np * np, 256)), 256, 0, s>>>(F, n, t.A, np);
   KFAC_LAUNCH_CHECK();
   KFAC_CUDA(cudaMemsetAsync(t.VT, 0, (size_t)np * np * 4, s));
   KFAC_CUDA(cudaMemsetAsync(t.Vp, 0, (size_t)np * TRD_NB * 4, s));

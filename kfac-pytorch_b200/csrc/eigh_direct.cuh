@@ -59,7 +59,9 @@ size_t stedc_plan_bytes(const int* n, int count);   // includes the grouped-GEMM
 // eigen-decomposition of `count` tridiagonal matrices; d_mats/h_mats describe them (device pointers inside);
 // plan_ws: device scratch of stedc_plan_bytes(); all work is enqueued on `s`
 // status: device int, bit 0 is set when a leaf QL iteration did not converge
-int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, int* status, cudaStream_t s);
+// q_zeroed: the caller has already zeroed Q[0] and Q[1] of every matrix
+int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, int* status, cudaStream_t s,
+                 bool q_zeroed = false);
 
 // plain fp32 TN GEMM on the tcgen05 engine: D = alpha * A B^T (+ D when accumulate)
 int gemm_tn_plain(const float* A, int64_t lda, const float* B, int64_t ldb, float* D, int64_t ldd, int M, int N,

@@ -534,7 +534,8 @@ size_t stedc_plan_bytes(const int* n, int count) {
          align_up(sizeof(DcMerge) * merges + 256 * (pl.levels.size() + 1), 256) + align_up(grouped_gemm_ws_bytes(2 * (int)widest), 256);
 }
 
-int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, int* status, cudaStream_t s) {
+int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t plan_bytes, int* status, cudaStream_t s,
+                 bool q_zeroed) {
   std::vector<int> ns(count);
   for (int i = 0; i < count; ++i) ns[i] = h_mats[i].n;
   Plan pl;
@@ -558,7 +559,7 @@ int launch_stedc(DcMat* h_mats, DcMat* d_mats, int count, void* plan_ws, size_t 
     KFAC_CUDA(cudaMemcpyAsync(d_levels[l], pl.levels[l].data(), sizeof(DcMerge) * pl.levels[l].size(),
                               cudaMemcpyHostToDevice, s));
   // Q buffers: off-diagonal blocks must be zero
-  for (int i = 0; i < count; ++i) {
+  for (int i = 0; i < count && !q_zeroed; ++i) {
     const size_t bytes = (size_t)h_mats[i].n * h_mats[i].ld * sizeof(float);
     KFAC_CUDA(cudaMemsetAsync(h_mats[i].Q[0], 0, bytes, s));
     KFAC_CUDA(cudaMemsetAsync(h_mats[i].Q[1], 0, bytes, s));
