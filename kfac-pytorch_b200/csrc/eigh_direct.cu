@@ -468,7 +468,7 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
 }  // namespace kfac
 
 // test / profiling entry (not in the public header): tridiagonalisation only
-extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e, float* VT, int ldv, float* tau,
+extern "C" int kfac_stage_sytrd(const float* F, int n, float* d, float* e, float* VT, int ldv, float* tau,
                                        void* ws, size_t ws_bytes, int ncta, void* stream) {
   using namespace kfac;
   cudaStream_t s = (cudaStream_t)stream;
@@ -509,7 +509,7 @@ extern "C" int kfac_experimental_sytrd(const float* F, int n, float* d, float* e
 }
 
 // test entry: D&C on a given tridiagonal (d, e) -> eigenvalues (ascending) and eigenvectors (columns of Q, ld n)
-extern "C" int kfac_experimental_stedc(const float* d_in, const float* e_in, int n, float* evals, float* Q, void* ws,
+extern "C" int kfac_stage_stedc(const float* d_in, const float* e_in, int n, float* evals, float* Q, void* ws,
                                        size_t ws_bytes, void* stream) {
   using namespace kfac;
   cudaStream_t s = (cudaStream_t)stream;
@@ -537,10 +537,10 @@ extern "C" int kfac_experimental_stedc(const float* d_in, const float* e_in, int
   return KFAC_OK;
 }
 
-extern "C" size_t kfac_experimental_direct_workspace_bytes(int n) {
+extern "C" size_t kfac_stage_direct_workspace_bytes(int n) {
   const int np = (n + 63) / 64 * 64;
   return (size_t)np * np * 4 * 5 + (size_t)np * 4096 + (1u << 22);
 }
 
 namespace kfac { int sytrd_profile(int on, unsigned long long* out16); }
-extern "C" int kfac_experimental_sytrd_profile(int on, unsigned long long* out16) { return kfac::sytrd_profile(on, out16); }
+extern "C" int kfac_stage_sytrd_profile(int on, unsigned long long* out16) { return kfac::sytrd_profile(on, out16); }

@@ -59,7 +59,7 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// optional phase timing (CTA 0, thread 0 of every group accumulates clock64 deltas): set by kfac_experimental_sytrd_profile
+// optional phase timing (CTA 0, thread 0 of every group accumulates clock64 deltas): set by kfac_stage_sytrd_profile
 __device__ unsigned long long g_trd_prof[16];
 __device__ int g_trd_prof_on = 0;
 #define TRD_STAMP(i) do { if (prof) { const long long t__ = clock64(); if (tid == 0) atomicAdd(&g_trd_prof[i], (unsigned long long)(t__ - tprev)); tprev = t__; } } while (0)

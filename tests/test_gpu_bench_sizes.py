@@ -69,6 +69,39 @@ def test_eigh_bench_sizes_cold_and_warm(n, m):
         QTprev.copy_(QT)
 
 
+def test_eigh_mixed_batch_one_call():
+    """One call over a mixed list -- the two shared-memory Jacobi classes, direct-solver sizes around every internal
+    boundary (leaf 64, dense/structured merges at 1024, 256-vector block reflectors) and a 6145-wide factor
+    (larger than anything in ResNet-50, not a multiple of 64): every result is checked against fp64."""
+    from kfac_b200 import _cabi
+    lib = _cabi.load()
+    dev = torch.device('cuda:0')
+    dims = [6145, 40, 128, 129, 191, 256, 257, 1000, 1025, 1088, 2047, 64]
+    mats = [next(iter(kfac_like_sequence(n, max(8, min(n, 512)), 1, dev))) for n in dims]
+    items = (_cabi.EighItem * len(dims))()
+    outs = []
+    for i, (n, F) in enumerate(zip(dims, mats)):
+        ld = _cabi.ld4(n)
+        Q, QT, d = torch.zeros(n, ld, device=dev), torch.zeros(n, ld, device=dev), torch.empty(n, device=dev)
+        outs.append((Q, QT, d))
+        items[i] = _cabi.EighItem(F.data_ptr(), Q.data_ptr(), QT.data_ptr(), d.data_ptr(), n, ld, None)
+    ns = (C.c_int * len(dims))(*dims)
+    need = lib.kfac_eigh_workspace_bytes(ns, len(dims))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    for rep in range(2):          # the second call reuses a dirty workspace
+        assert lib.kfac_eigh_batched(items, len(dims), ws.data_ptr(), need, 0, 0.0, s) == 0, lib.kfac_last_error()
+    host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    assert lib.kfac_eigh_status(ws.data_ptr(), host.data_ptr(), s) == 0
+    torch.cuda.synchronize()
+    assert int(host[0]) == 0
+    for n, F, (Q, QT, d) in zip(dims, mats, outs):
+        r = _check_against_fp64(F, Q[:, :n], d)
+        print(f'mixed batch n={n}: {r}')
+        assert r['orth'] < 2e-4 and r['f_err'] < 1e-3 and r['eigval'] < 5e-5, (n, r)
+        assert torch.equal(QT[:, :n], Q[:, :n].t())
+
+
 def _parity_full(make_model, batches, loss_fn, **kw):
     """Full-model parity vs the CPU oracle: same raw gradients fed to both, per-layer A, G, P compared."""
     from kfac_b200.preconditioner import KFACPreconditioner

@@ -14,14 +14,14 @@ pytestmark = pytest.mark.gpu
 def lib():
     from kfac_b200 import _cabi
     lib = _cabi.load()
-    lib.kfac_experimental_sytrd.restype = C.c_int
-    lib.kfac_experimental_sytrd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+    lib.kfac_stage_sytrd.restype = C.c_int
+    lib.kfac_stage_sytrd.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
-    lib.kfac_experimental_stedc.restype = C.c_int
-    lib.kfac_experimental_stedc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+    lib.kfac_stage_stedc.restype = C.c_int
+    lib.kfac_stage_stedc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                             C.c_void_p]
-    lib.kfac_experimental_direct_workspace_bytes.restype = C.c_size_t
-    lib.kfac_experimental_direct_workspace_bytes.argtypes = [C.c_int]
+    lib.kfac_stage_direct_workspace_bytes.restype = C.c_size_t
+    lib.kfac_stage_direct_workspace_bytes.argtypes = [C.c_int]
     return lib
 
 
@@ -49,12 +49,12 @@ def run_sytrd(lib, F, ncta):
     e = torch.zeros(n, device=dev)
     tau = torch.zeros(n, device=dev)
     VT = torch.zeros(n, n, device=dev)
-    need = lib.kfac_experimental_direct_workspace_bytes(n)
+    need = lib.kfac_stage_direct_workspace_bytes(n)
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for rep in range(2):
         e0.record()
-        rc = lib.kfac_experimental_sytrd(Fd.data_ptr(), n, d.data_ptr(), e.data_ptr(), VT.data_ptr(), n, tau.data_ptr(),
+        rc = lib.kfac_stage_sytrd(Fd.data_ptr(), n, d.data_ptr(), e.data_ptr(), VT.data_ptr(), n, tau.data_ptr(),
                                          ws.data_ptr(), need, ncta, S())
         e1.record()
         assert rc == 0, lib.kfac_last_error()
@@ -117,12 +117,12 @@ def test_stedc(lib, n, kind):
     dd, ed = d.to(dev), e.to(dev)
     ev = torch.zeros(n, device=dev)
     Q = torch.zeros(n, n, device=dev)
-    need = lib.kfac_experimental_direct_workspace_bytes(n)
+    need = lib.kfac_stage_direct_workspace_bytes(n)
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for rep in range(2):
         e0.record()
-        rc = lib.kfac_experimental_stedc(dd.data_ptr(), ed.data_ptr(), n, ev.data_ptr(), Q.data_ptr(), ws.data_ptr(), need, S())
+        rc = lib.kfac_stage_stedc(dd.data_ptr(), ed.data_ptr(), n, ev.data_ptr(), Q.data_ptr(), ws.data_ptr(), need, S())
         e1.record()
         assert rc == 0, lib.kfac_last_error()
         torch.cuda.synchronize()
