@@ -286,8 +286,8 @@ def run_b200(args):
     crit = torch.nn.CrossEntropyLoss()
     timer = PhaseTimer(pre)
 
-    # NB distinct pre-generated batches, cycled: every step sees new statistics (a single repeated batch lets a
-    # warm-started iterative eigensolver converge in 1-3 sweeps, which the CPU arm's LAPACK cost does not see)
+    # NB distinct pre-generated batches, cycled: every step sees new statistics (round 1 fed a single repeated batch,
+    # which flattered its warm-started iterative eigensolver; the direct solver's cost does not depend on the data)
     torch.manual_seed(1 + rank)
     B = shape[0]
     NB = max(1, args.batches)

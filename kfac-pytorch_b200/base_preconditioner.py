@@ -275,8 +275,7 @@ class BaseKFACPreconditioner:
         _cabi.load()
         self._device = device
         ll = self._layer_list()
-        # dense d x d factors, each starting 16-byte aligned (they are TMA operands of the
-        # warm-start GEMM G = F V0)
+        # dense d x d factors, each starting 16-byte aligned
         total = sum(_cabi.ld4(l.a_dim ** 2) + _cabi.ld4(l.g_dim ** 2) for _, l in ll)
         self._factor_arena = torch.zeros(total, dtype=torch.float32, device=device)
         self._batch_arena = torch.zeros(total, dtype=torch.float32, device=device)
