@@ -120,6 +120,7 @@ typedef struct kfac_eigh_item {
   int ldq;        /* 0 -> n.  Multiples of 4 let the tensor-core GEMMs consume Q directly */
   const float* V0T; /* ignored (warm start of the round-1 iterative solver; kept for ABI compatibility) */
 } kfac_eigh_item;
+#define KFAC_EIGH_MAX_N 8192   /* largest factor dimension (KFAC_ERR_UNSUPPORTED beyond) */
 size_t kfac_eigh_workspace_bytes(const int* n, int count);
 /* max_sweeps <= 0 -> default (24 sweeps of the n <= 128 Jacobi); tol is ignored.
  * The first int of the workspace is a device status word written by the call (0 = fine, bit 0 = an

@@ -301,7 +301,15 @@ size_t eigh_direct_workspace_bytes(const int* n, int count) {
 int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_bytes, int* status, cudaStream_t s) {
   if (count <= 0) return KFAC_OK;
   std::vector<int> ns(count);
-  for (int i = 0; i < count; ++i) ns[i] = items[i].n;
+  for (int i = 0; i < count; ++i) {
+    ns[i] = items[i].n;
+    // limits of the stages: the deflation scan of the top-level merge sorts n values in shared memory (6 n floats),
+    // the tile lists of the tridiagonalisation hold 256 entries per sub-group
+    if (ns[i] > KFAC_EIGH_MAX_N) {
+      set_error("eigh(direct): n = %d exceeds the supported dimension %d", ns[i], KFAC_EIGH_MAX_N);
+      return KFAC_ERR_UNSUPPORTED;
+    }
+  }
   Layout L;
   make_layout(ns.data(), count, L);
   if (!ws || ws_bytes < L.total) { set_error("eigh(direct): workspace too small (%zu < %zu)", ws_bytes, L.total); return KFAC_ERR_WORKSPACE; }

@@ -462,7 +462,9 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
             if (b0 + warp < nblk) g0 = __ldcg(pp);
             if (b0 + warp + 32 < nblk) g1 = __ldcg(pp + (int64_t)32 * np);
             if (b0 + warp + 64 < nblk) g2 = __ldcg(pp + (int64_t)64 * np);
-            g[q] = (g0 + g1) + g2;
+            float gx = 0.f;                            // more than 96 active tile classes: n > 6144 only
+            for (int X = b0 + warp + 96; X < nblk; X += 32) gx += __ldcg(mt.part + (int64_t)X * np + rl);
+            g[q] = ((g0 + g1) + g2) + gx;
           }
         }
       };
@@ -492,6 +494,7 @@ __device__ void tridiagonalise(const TrdMat& mt, int cta, int ncta, float* smem)
         if (warp == 1) {
 #pragma unroll
           for (int j = 0; j < 3; ++j) { const int X = b0 + lane + 32 * j; if (X < nblk) y1p += __ldcg(&mt.part[(int64_t)X * np + s1]); }
+          for (int X = b0 + lane + 96; X < nblk; X += 32) y1p += __ldcg(&mt.part[(int64_t)X * np + s1]);    // n > 6144
           if (lane < P) { vrow = __ldcg(mt.Vp + s1 * NB + lane); wrow = __ldcg(mt.Wp + s1 * NB + lane); }
           a11 = __ldcg(&A[(int64_t)s1 * np + s1]);
         }

@@ -249,6 +249,22 @@ def test_eigh_large(lib, dev):
         check_eigh(F, Q, d)
 
 
+def test_eigh_rejects_oversized(lib, dev):
+    """Dimensions beyond KFAC_EIGH_MAX_N (8192) are refused up front with KFAC_ERR_UNSUPPORTED, not solved wrongly."""
+    from kfac_b200 import _cabi
+    n = 8193
+    ns = (C.c_int * 1)(n)
+    need = lib.kfac_eigh_workspace_bytes(ns, 1)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    ld = _cabi.ld4(n)
+    F = torch.eye(n, device=dev)
+    Q = torch.zeros(n, ld, device=dev)
+    d = torch.empty(n, device=dev)
+    items = (_cabi.EighItem * 1)(_cabi.EighItem(F.data_ptr(), Q.data_ptr(), None, d.data_ptr(), n, ld, None))
+    rc = lib.kfac_eigh_batched(items, 1, ws.data_ptr(), need, 0, 0.0, S())
+    assert rc != 0 and b'exceeds the supported dimension' in lib.kfac_last_error()
+
+
 def test_eigh_reports_non_finite_input(lib, dev):
     """A factor with an Inf (AMP overflow step) must not yield a silently wrong eigenbasis: the status word of
     the workspace reports it (torch.linalg.eigh raises in the reference, kfac/layers/eigen.py:310)."""
