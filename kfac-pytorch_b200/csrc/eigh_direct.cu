@@ -309,6 +309,11 @@ int eigh_direct_run(const kfac_eigh_item* items, int count, void* ws, size_t ws_
       set_error("eigh(direct): n = %d exceeds the supported dimension %d", ns[i], KFAC_EIGH_MAX_N);
       return KFAC_ERR_UNSUPPORTED;
     }
+    if (sytrd_min_ctas(ns[i]) > sytrd_max_grid()) {
+      set_error("eigh(direct): n = %d needs %d CTAs for its tile lists, the device has %d SMs", ns[i], sytrd_min_ctas(ns[i]),
+                sytrd_max_grid());
+      return KFAC_ERR_UNSUPPORTED;
+    }
   }
   Layout L;
   make_layout(ns.data(), count, L);
@@ -549,6 +554,18 @@ extern "C" size_t kfac_stage_direct_workspace_bytes(int n) {
   const int np = (n + 63) / 64 * 64;
   return (size_t)np * np * 4 * 5 + (size_t)np * 4096 + (1u << 22);
 }
+
+// host-only: the CTA-group schedule of the tridiagonalisation kernel for a list of dimensions on `grid` CTAs
+// (no device needed: tests/test_host_logic.py checks coverage, ranges and that the job order cannot deadlock)
+extern "C" int kfac_stage_schedule(const int* n, int count, int grid, int* mat, int* cta0, int* ncta) {
+  using namespace kfac;
+  if (!n || count <= 0 || grid <= 0) return 0;
+  std::vector<TrdJob> jobs;
+  make_schedule(n, count, grid, jobs);
+  for (size_t i = 0; i < jobs.size(); ++i) { mat[i] = jobs[i].mat; cta0[i] = jobs[i].cta0; ncta[i] = jobs[i].ncta; }
+  return (int)jobs.size();
+}
+extern "C" int kfac_stage_sytrd_min_ctas(int n) { return kfac::sytrd_min_ctas(n); }
 
 namespace kfac { int sytrd_profile(int on, unsigned long long* out16); }
 extern "C" int kfac_stage_sytrd_profile(int on, unsigned long long* out16) { return kfac::sytrd_profile(on, out16); }

@@ -240,3 +240,46 @@ def test_bench_cpu_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2'],
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == '', (out.stdout[-500:], out.stderr[-500:])
+
+
+def test_sytrd_schedule_covers_all_and_cannot_deadlock():
+    """The tridiagonalisation kernel is ONE cooperative launch in which every CTA walks the job list front to back
+    and spins at group barriers: the host-side schedule must (i) place every matrix exactly once on a CTA range inside
+    the grid, at least as wide as the kernel's tile lists need, and (ii) order the jobs so that the walk always makes
+    progress.  Checked by simulating the walk (host-only entry of the library, no GPU)."""
+    from kfac_b200 import _cabi
+    lib = _cabi.load()
+    lib.kfac_stage_schedule.restype = ctypes.c_int
+    lib.kfac_stage_sytrd_min_ctas.restype = ctypes.c_int
+    r50 = [(147, 64, 1), (64, 64, 1), (64, 256, 4), (256, 64, 2), (576, 64, 3), (128, 512, 4), (256, 128, 1),
+           (256, 512, 1), (512, 128, 3), (1152, 128, 4), (256, 1024, 6), (512, 256, 1), (512, 1024, 1), (1024, 256, 5),
+           (2304, 256, 6), (512, 2048, 3), (1024, 512, 1), (1024, 2048, 1), (2048, 512, 2), (4608, 512, 3), (2049, 1000, 1)]
+    cases = [[d for a, g, c in r50 for d in [a, g] * c if d > 128], [4608], [8192, 130], [300] * 200, [2304, 2304, 129]]
+    for dims in cases:
+        for grid in (148, 132, 16):
+            count = len(dims)
+            n = (ctypes.c_int * count)(*dims)
+            mat, cta0, ncta = ((ctypes.c_int * count)() for _ in range(3))
+            jobs = lib.kfac_stage_schedule(n, count, grid, mat, cta0, ncta)
+            assert jobs == count
+            assert sorted(mat[i] for i in range(jobs)) == list(range(count))
+            queues = [[] for _ in range(grid)]
+            for j in range(jobs):
+                need = min(grid, lib.kfac_stage_sytrd_min_ctas(dims[mat[j]]))
+                assert 0 <= cta0[j] and cta0[j] + ncta[j] <= grid and ncta[j] >= need, (dims[mat[j]], cta0[j], ncta[j])
+                for c in range(cta0[j], cta0[j] + ncta[j]):
+                    queues[c].append(j)
+            # a job runs when it is at the head of the queue of every CTA of its group
+            head = [0] * grid
+            done = 0
+            progress = True
+            while progress:
+                progress = False
+                for j in range(jobs):
+                    cs = range(cta0[j], cta0[j] + ncta[j])
+                    if all(head[c] < len(queues[c]) and queues[c][head[c]] == j for c in cs):
+                        for c in cs:
+                            head[c] += 1
+                        done += 1
+                        progress = True
+            assert done == jobs, f'schedule deadlocks: {done} of {jobs} jobs can run (grid {grid})'
