@@ -451,6 +451,19 @@ def run_b200(args):
             traffic = tr.get('dram_bytes_per_call')
     except Exception:  # noqa: BLE001
         pass
+    # the same launch seen from the memory side: the tridiagonalisation streams the trailing matrices once per column,
+    # so the MEASURED DRAM bytes of the call (not the 12 n^2 algorithmic ones) over its time, against the measured copy
+    # bandwidth, say how far the dominant kernel is from the HBM bound
+    hbm_view = None
+    try:
+        if traffic and inv_ms > 0:
+            hbm_peak = float(peaks.get('hbm_gbs', 7700.0))
+            gbs = float(traffic) / (inv_ms / 1e3) / 1e9
+            hbm_view = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                        'note': 'measured dram bytes of one kfac_eigh_batched call (profiles/eigh_traffic.json) / its '
+                                'CUDA-event time; 90 % of the bytes belong to sytrd_kernel (profiles/r02_launches_eigh_batch.md)'}
+    except Exception:  # noqa: BLE001
+        hbm_view = None
     out = {
         'metric': metric_name(args.model), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_dev / K, 'higher_is_better': True,
@@ -487,6 +500,7 @@ def run_b200(args):
                                    "rank's factors / CUDA-event time of the call; algorithmic bytes 3*4*n^2 per factor; "
                                    'traffic = dram__bytes_read+write of all kernels of one call (profiles/eigh_traffic.json)',
                      'peak_source': peak_src},
+        'roofline_hbm_view': hbm_view,
         # the GEMM engine all tensor-core kernels instantiate, timed alone on a 4096^3 problem
         'roofline_engine': {'kernel': 'tc::pipeline_kernel<GemmPolicy> (tcgen05 3xTF32 GEMM engine), 4096^3, isolated',
                             'bound': 'tensor', 'achieved': gemm_tf, 'peak': burst_peak, 'unit': 'TFLOP/s',
