@@ -834,6 +834,10 @@ class BaseKFACPreconditioner:
 
     # ------------------------------------------------------------ misc API
     def reset_batch(self) -> None:
+        if self._a_reduce_work is not None:      # an overlapped all-reduce of the A block must not race with the zeroing
+            self._a_reduce_work.wait()
+            self._a_reduce_work = None
+        self._a_block_reduced = False
         for _, layer in self._layers.values():
             layer.reset_batch()
         self._pending_alpha = {}
